@@ -1,0 +1,391 @@
+// extern "C" entry points of include/hwer_b200.h: argument checking, workspace
+// management, the TMA tensor map, and the round schedule of the fused
+// score-and-select (filter -> select ... -> final).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/hwer_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return HWER_E_CUDA;
+}
+#define HWER_CUDA(call)                                    \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+long long gcd_ll(long long a, long long b) {
+    while (b) { long long t = a % b; a = b; b = t; }
+    return a;
+}
+
+}  // namespace
+
+struct hwer_index {
+    int device = 0;
+    int num_sms = 0;
+    const float* table = nullptr;
+    const void* shadow = nullptr;
+    long long n = 0;
+    int d = 0, d_pad = 0;
+    float max_norm = 1.0f;
+    bool use_tc = false;
+    CUtensorMap tmap;
+    long long n_tiles = 0;
+    long long tile_mul = 1;
+    // workspace, grown on demand
+    unsigned long long* cand = nullptr;
+    unsigned int* cnt = nullptr;
+    float* thr = nullptr;
+    float* margin = nullptr;
+    size_t ws_queries = 0, ws_cap = 0;
+    unsigned int* needed_dev = nullptr;
+    unsigned int* needed_host = nullptr;   // pinned
+    unsigned int last_cap = 0;
+};
+
+namespace {
+
+int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
+    if (queries <= ix->ws_queries && cap <= ix->ws_cap) return HWER_OK;
+    HWER_CUDA(cudaDeviceSynchronize());
+    if (ix->cand) cudaFree(ix->cand);
+    if (ix->cnt) cudaFree(ix->cnt);
+    if (ix->thr) cudaFree(ix->thr);
+    if (ix->margin) cudaFree(ix->margin);
+    ix->cand = nullptr; ix->cnt = nullptr; ix->thr = nullptr; ix->margin = nullptr;
+    ix->ws_queries = ix->ws_cap = 0;
+    const size_t q = queries > ix->ws_queries ? queries : ix->ws_queries;
+    const size_t c = cap > ix->ws_cap ? cap : ix->ws_cap;
+    if (cudaMalloc(&ix->cand, q * c * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ix->cnt, q * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&ix->thr, q * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&ix->margin, q * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HWER_E_NOMEM, "hwer_topk: cannot allocate the candidate workspace");
+    }
+    ix->ws_queries = q;
+    ix->ws_cap = c;
+    return HWER_OK;
+}
+
+struct Schedule {
+    int growth;
+    unsigned int cap;
+    long long first_tiles;
+};
+
+// Round schedule: round 0 scores `first_tiles` tiles with an open threshold; each later round scores
+// `growth` times what has been seen, so it admits about k * growth candidates per query.
+int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
+    const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
+    long long first_rows = 1024;
+    if (first_rows < 2LL * k) first_rows = 2LL * k;
+    s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
+    first_rows = s->first_tiles * hwer::kTileItems;
+    int g = (B <= 256) ? 16 : 8;
+    while (g > 2 && 3LL * k * g > max_cap) g >>= 1;
+    unsigned long long want = 3ULL * k * g;
+    if (want < (unsigned long long)first_rows) want = first_rows;
+    if (cap_user) {
+        if (cap_user < first_rows) return fail(HWER_E_INVALID, "hwer_topk: cap smaller than the first round");
+        want = cap_user;
+    }
+    unsigned long long cap = 1024;
+    while (cap < want) cap <<= 1;
+    if (cap > max_cap) return fail(HWER_E_INVALID, "hwer_topk: k (or cap) too large for the shared-memory selector");
+    s->growth = g;
+    s->cap = (unsigned int)cap;
+    return HWER_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hwer_last_error(void) { return g_err.c_str(); }
+int hwer_version(void) { return 100; }
+int32_t hwer_shadow_width(int32_t d) { return (d + 63) / 64 * 64; }
+
+int hwer_blend_normalize(const float* content_dev, const float* collab_dev, float alpha, const float* alpha_rows_dev,
+                         int64_t n, int32_t d, float* out_f32_dev, void* out_bf16_dev, int32_t d_pad, void* stream) {
+    if (!collab_dev || !out_f32_dev || n < 0 || d <= 0) return fail(HWER_E_INVALID, "hwer_blend_normalize: bad argument");
+    if (out_bf16_dev && d_pad < d) return fail(HWER_E_INVALID, "hwer_blend_normalize: d_pad < d");
+    HWER_CUDA(hwer::launch_blend_normalize(content_dev, collab_dev, alpha, alpha_rows_dev, n, d, out_f32_dev,
+                                           out_bf16_dev, d_pad, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_make_shadow(const float* table_dev, int64_t n, int32_t d, void* out_bf16_dev, int32_t d_pad, void* stream) {
+    if (!table_dev || !out_bf16_dev || n <= 0 || d <= 0 || d_pad < d || d_pad % 2)
+        return fail(HWER_E_INVALID, "hwer_make_shadow: bad argument");
+    HWER_CUDA(hwer::launch_make_shadow(table_dev, n, d, out_bf16_dev, d_pad, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_norm_stats(const float* table_dev, int64_t n, int32_t d, float epsilon, double* out5_dev, void* stream) {
+    if (!table_dev || !out5_dev || n <= 0 || d <= 0) return fail(HWER_E_INVALID, "hwer_norm_stats: bad argument");
+    HWER_CUDA(hwer::launch_norm_stats(table_dev, n, d, epsilon, out5_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_index_create(hwer_index_t** out, const float* table_f32_dev, const void* shadow_bf16_dev, int64_t n,
+                      int32_t d, int32_t d_pad, float max_norm, int32_t device) {
+    if (!out || !table_f32_dev || n <= 0 || d <= 0) return fail(HWER_E_INVALID, "hwer_index_create: bad argument");
+    if (n >= (1LL << 31) - 256) return fail(HWER_E_INVALID, "hwer_index_create: shard too large (rows must fit 31 bits)");
+    HWER_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HWER_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(HWER_E_ARCH, "hwer_index_create: device is not sm_100 (B200)");
+    hwer_index* ix = new hwer_index();
+    ix->device = device;
+    ix->num_sms = prop.multiProcessorCount;
+    ix->table = table_f32_dev;
+    ix->shadow = shadow_bf16_dev;
+    ix->n = n;
+    ix->d = d;
+    ix->d_pad = d_pad;
+    ix->max_norm = (max_norm > 0.0f && max_norm == max_norm) ? max_norm : 1.0f;
+    ix->n_tiles = (n + hwer::kTileItems - 1) / hwer::kTileItems;
+    ix->use_tc = shadow_bf16_dev != nullptr && d_pad >= d && d_pad % 64 == 0 && d_pad <= 256;
+    if (shadow_bf16_dev && !ix->use_tc && d_pad <= 256) {
+        delete ix;
+        return fail(HWER_E_INVALID, "hwer_index_create: d_pad must be a multiple of 64 and >= d");
+    }
+    if (ix->use_tc) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) { delete ix; return fail(HWER_E_CUDA, "cuTensorMapEncodeTiled entry point not found"); }
+        cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)n};
+        cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+        cuuint32_t box[2] = {(cuuint32_t)hwer::kKBlock, (cuuint32_t)hwer::kTileItems};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&ix->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(shadow_bf16_dev), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            delete ix;
+            char buf[96];
+            snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+            return fail(HWER_E_CUDA, buf);
+        }
+        // Visit tiles in a scrambled order so early rounds sample the whole catalogue even when rows are
+        // sorted (clustered catalogues): tile t -> (t * mul) mod n_tiles with gcd(mul, n_tiles) = 1.
+        long long mul = (long long)((double)ix->n_tiles * 0.6180339887) | 1;
+        while (mul > 1 && gcd_ll(mul, ix->n_tiles) != 1) mul -= 2;
+        if (mul < 1 || ix->n_tiles < 8) mul = 1;
+        ix->tile_mul = mul;
+    }
+    if (cudaMalloc(&ix->needed_dev, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMallocHost(&ix->needed_host, sizeof(unsigned int)) != cudaSuccess) {
+        delete ix;
+        return fail(HWER_E_NOMEM, "hwer_index_create: allocation failed");
+    }
+    cudaMemset(ix->needed_dev, 0, sizeof(unsigned int));
+    *ix->needed_host = 0;
+    *out = ix;
+    return HWER_OK;
+}
+
+int hwer_index_destroy(hwer_index_t* ix) {
+    if (!ix) return HWER_OK;
+    cudaSetDevice(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->cand) cudaFree(ix->cand);
+    if (ix->cnt) cudaFree(ix->cnt);
+    if (ix->thr) cudaFree(ix->thr);
+    if (ix->margin) cudaFree(ix->margin);
+    if (ix->needed_dev) cudaFree(ix->needed_dev);
+    if (ix->needed_host) cudaFreeHost(ix->needed_host);
+    delete ix;
+    return HWER_OK;
+}
+
+int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
+              int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream_v) {
+    if (!ix || B < 0 || k <= 0 || (B > 0 && (!queries_dev || !out_idx_dev || !out_score_dev)))
+        return fail(HWER_E_INVALID, "hwer_topk: bad argument");
+    if (mode != HWER_MODE_EXACT && mode != HWER_MODE_BF16) return fail(HWER_E_INVALID, "hwer_topk: unknown mode");
+    if (mode == HWER_MODE_BF16 && !ix->use_tc)
+        return fail(HWER_E_INVALID, "hwer_topk: bf16 mode needs a bf16 shadow table (d_pad <= 256)");
+    if ((long long)k > ix->n) return fail(HWER_E_K_TOO_LARGE, "hwer_topk: k exceeds the number of rows in the index");
+    if (B == 0) return HWER_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    HWER_CUDA(cudaSetDevice(ix->device));
+
+    Schedule sch;
+    int rc = make_schedule(B, k, cap, &sch);
+    if (rc) return rc;
+    // bound the candidate workspace to ~1 GiB by chunking the query batch
+    size_t chunk = ((size_t)1 << 30) / ((size_t)sch.cap * 8);
+    chunk = chunk / 256 * 256;
+    if (chunk < 256) chunk = 256;
+    if (chunk > (size_t)B) chunk = B;
+    rc = ensure_workspace(ix, chunk, sch.cap);
+    if (rc) return rc;
+    ix->last_cap = sch.cap;
+
+    const bool exact = mode == HWER_MODE_EXACT;
+    const float eps_rel = ix->use_tc ? hwer::bf16_score_eps_rel(ix->d_pad) : hwer::f32_score_eps_rel(ix->d);
+    const float margin_factor = 2.0f * eps_rel * ix->max_norm * 1.0001f;
+    const long long T = ix->n_tiles;
+
+    for (long long q0 = 0; q0 < B; q0 += (long long)chunk) {
+        const int Bc = (int)(((long long)B - q0) < (long long)chunk ? ((long long)B - q0) : (long long)chunk);
+        const float* Q = queries_dev + (size_t)q0 * ix->d;
+        HWER_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(unsigned int) * Bc, stream));
+        HWER_CUDA(hwer::launch_fill_f32(ix->thr, Bc, -INFINITY, stream));
+        const float* margin = nullptr;
+        if (exact || !ix->use_tc) {
+            // the CUDA-core path scores in fp32: its (tiny) margin keeps even bf16-less indexes exact
+            HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->margin, stream));
+            margin = ix->margin;
+        }
+        long long seen = 0;
+        int round = 0;
+        while (seen < T) {
+            long long take = round == 0 ? sch.first_tiles : seen * sch.growth;
+            long long end = seen + take;
+            if (end > T || (T - end) * 4 < take) end = T;
+            if (ix->use_tc) {
+                hwer::FilterParams p;
+                memset(&p, 0, sizeof p);
+                p.queries = Q; p.B = Bc; p.d = ix->d; p.kb = ix->d_pad / 64;
+                int nq = (Bc + 15) / 16 * 16;
+                const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
+                if (nq > nq_max) nq = nq_max;
+                p.nq = nq; p.nqb = (Bc + nq - 1) / nq;
+                p.thr = ix->thr; p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
+                p.n_items = ix->n; p.tile_begin = (int)seen; p.tile_end = (int)end;
+                p.tile_mul = ix->tile_mul; p.tile_mod = T;
+                HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
+            } else {
+                long long rb = seen * hwer::kTileItems, re = end * hwer::kTileItems;
+                if (re > ix->n) re = ix->n;
+                HWER_CUDA(hwer::launch_filter_simt(ix->table, ix->n, ix->d, Q, Bc, ix->thr, ix->cand, ix->cnt, sch.cap,
+                                                   rb, re, ix->num_sms, stream));
+            }
+            HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, margin, ix->thr, ix->needed_dev,
+                                                  stream));
+            seen = end;
+            ++round;
+        }
+        HWER_CUDA(hwer::launch_final(ix->cand, ix->cnt, sch.cap, Bc, k, exact ? 1 : 0, ix->table, ix->d, Q, idx_offset,
+                                     (long long*)out_idx_dev + (size_t)q0 * k, out_score_dev + (size_t)q0 * k,
+                                     out_score64_dev ? out_score64_dev + (size_t)q0 * k : nullptr, ix->needed_dev,
+                                     stream));
+    }
+    return HWER_OK;
+}
+
+int hwer_topk_finish(hwer_index_t* ix, void* stream_v, uint32_t* needed_cap) {
+    if (!ix) return fail(HWER_E_INVALID, "hwer_topk_finish: null index");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    HWER_CUDA(cudaSetDevice(ix->device));
+    HWER_CUDA(cudaMemcpyAsync(ix->needed_host, ix->needed_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    HWER_CUDA(cudaMemsetAsync(ix->needed_dev, 0, sizeof(unsigned int), stream));
+    HWER_CUDA(cudaStreamSynchronize(stream));
+    const unsigned int need = *ix->needed_host;
+    if (needed_cap) *needed_cap = need;
+    if (need > ix->last_cap) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "hwer_topk: candidate lists overflowed (cap %u, needed %u): re-run with a larger cap",
+                 ix->last_cap, need);
+        return fail(HWER_E_OVERFLOW, buf);
+    }
+    return HWER_OK;
+}
+
+int hwer_debug_scores(hwer_index_t* ix, const float* queries_dev, int32_t B, float* out_dev, int64_t ld, void* stream) {
+    if (!ix || !ix->use_tc || !queries_dev || !out_dev || B <= 0 || ld < B)
+        return fail(HWER_E_INVALID, "hwer_debug_scores: bad argument");
+    HWER_CUDA(cudaSetDevice(ix->device));
+    hwer::FilterParams p;
+    memset(&p, 0, sizeof p);
+    p.queries = queries_dev; p.B = B; p.d = ix->d; p.kb = ix->d_pad / 64;
+    int nq = (B + 15) / 16 * 16;
+    const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
+    if (nq > nq_max) nq = nq_max;
+    p.nq = nq; p.nqb = (B + nq - 1) / nq;
+    p.n_items = ix->n; p.tile_begin = 0; p.tile_end = (int)ix->n_tiles;
+    p.tile_mul = ix->tile_mul; p.tile_mod = ix->n_tiles;
+    p.dump = out_dev; p.dump_ld = ld;
+    HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_merge_topk(const double* scores_dev, const int64_t* idx_dev, int32_t G, int32_t B, int32_t k,
+                    int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream) {
+    if (!scores_dev || !idx_dev || G <= 0 || B < 0 || k <= 0 || !out_idx_dev || !out_score_dev)
+        return fail(HWER_E_INVALID, "hwer_merge_topk: bad argument");
+    HWER_CUDA(hwer::launch_merge(scores_dev, (const long long*)idx_dev, G, B, k, (long long*)out_idx_dev,
+                                 out_score_dev, out_score64_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t* src_dev, const int64_t* dst_dev,
+                    int64_t P, float* out_dev, void* stream) {
+    if (!table_dev || n <= 0 || d <= 0 || P < 0 || (P > 0 && (!src_dev || !dst_dev || !out_dev)))
+        return fail(HWER_E_INVALID, "hwer_pair_score: bad argument");
+    HWER_CUDA(hwer::launch_pair_score(table_dev, n, d, (const long long*)src_dev, (const long long*)dst_dev, P,
+                                      out_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_eval_metrics(const int64_t* topk_dev, int32_t U, int32_t kret, const int64_t* train_ptr_dev,
+                      const int64_t* train_idx_dev, const int64_t* val_ptr_dev, const int64_t* val_idx_dev,
+                      const float* val_rel_dev, const int32_t* cutoffs_dev, int32_t n_cut, int64_t n_items,
+                      double* out_dev, double* per_user_dev, void* stream_v) {
+    if (!topk_dev || U <= 0 || kret <= 0 || !train_ptr_dev || !val_ptr_dev || !cutoffs_dev || n_cut <= 0 ||
+        n_cut > 8 || n_items <= 0 || !out_dev)
+        return fail(HWER_E_INVALID, "hwer_eval_metrics: bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int M = 3 * n_cut + 1;
+    double* per_user = per_user_dev;
+    if (!per_user) HWER_CUDA(cudaMallocAsync(&per_user, sizeof(double) * (size_t)U * M, stream));
+    unsigned int* bitmap = nullptr;
+    const size_t words = (size_t)((n_items + 31) / 32);
+    HWER_CUDA(cudaMallocAsync(&bitmap, sizeof(unsigned int) * words, stream));
+    HWER_CUDA(cudaMemsetAsync(bitmap, 0, sizeof(unsigned int) * words, stream));
+    HWER_CUDA(hwer::launch_eval((const long long*)topk_dev, U, kret, (const long long*)train_ptr_dev,
+                                (const long long*)train_idx_dev, (const long long*)val_ptr_dev,
+                                (const long long*)val_idx_dev, val_rel_dev, cutoffs_dev, n_cut, n_items, per_user,
+                                bitmap, stream));
+    HWER_CUDA(hwer::launch_eval_reduce(per_user, U, M, (const long long*)val_ptr_dev, bitmap, n_items, n_cut, out_dev,
+                                       stream));
+    HWER_CUDA(cudaFreeAsync(bitmap, stream));
+    if (!per_user_dev) HWER_CUDA(cudaFreeAsync(per_user, stream));
+    return HWER_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Internal launcher declarations (C++ side of the C-ABI in include/hwer_b200.h).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hwer {
+
+constexpr int kTileItems = 128;      // catalogue rows per tcgen05 tile (UMMA M)
+constexpr int kKBlock = 64;          // bf16 elements per 128-byte swizzled smem row
+constexpr int kMaxNQ = 256;          // queries per CTA-resident query block (UMMA N)
+constexpr int kSmemBudget = 227 * 1024;
+
+// Proven bound on |bf16-tensor-core score - exact score| / (|q| * |x|):
+// two round-to-nearest bf16 roundings (2^-9 each) plus fp32 accumulation of
+// d_pad products.  See DESIGN.md "Exactness".
+inline float bf16_score_eps_rel(int d_pad) {
+    return 0.00390625f + 3.8147e-6f + float(d_pad) * 2.3841858e-7f;
+}
+inline float f32_score_eps_rel(int d) { return float(d) * 2.3841858e-7f; }
+
+struct FilterParams {
+    const float* queries;     // [B, d] fp32, device
+    int B;
+    int d;                    // logical embedding width
+    int kb;                   // d_pad / 64
+    int nq;                   // queries per block (multiple of 16, <= 256)
+    int nqb;                  // number of query blocks = ceil(B / nq)
+    int slots;                // CTAs cooperating on one query block (split of the item tiles)
+    int qb_step;              // query blocks advanced per outer iteration (= gridDim.x / slots)
+    const float* thr;         // [B] current per-query admission threshold
+    unsigned long long* cand; // [B, cap] packed candidate keys
+    unsigned int* cnt;        // [B] candidate counters (may exceed cap => overflow)
+    unsigned int cap;
+    long long n_items;
+    int tile_begin, tile_end; // item-tile range of this round (positions in the visiting order)
+    long long tile_mul;       // visiting order: physical tile = (position * tile_mul) % tile_mod
+    long long tile_mod;
+    int stages;               // smem pipeline depth
+    int acc_stages;           // TMEM accumulator stages
+    int tmem_cols;            // power of two >= acc_stages * nq
+    int stream_once;          // 1: item tiles are read by one CTA only -> L2 evict-first
+    float* dump;              // debug: full score matrix [n_items, dump_ld] (nullptr in production)
+    long long dump_ld;
+};
+
+cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sms, cudaStream_t stream);
+size_t filter_tc_smem_bytes(int nq, int kb, int stages);
+int filter_tc_pick_stages(int nq, int kb);
+
+// Generic CUDA-core variant for widths the tensor-core tile does not cover (d_pad > 256).
+cudaError_t launch_filter_simt(const float* table, long long n_items, int d, const float* queries, int B,
+                               const float* thr, unsigned long long* cand, unsigned int* cnt, unsigned int cap,
+                               long long row_begin, long long row_end, int num_sms, cudaStream_t stream);
+
+cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float* margin,
+                                cudaStream_t stream);
+cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream);
+
+cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
+                                  const float* margin, float* thr, unsigned int* needed_cap, cudaStream_t stream);
+
+cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
+                         int exact, const float* table, int d, const float* queries, long long idx_offset,
+                         long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
+                         cudaStream_t stream);
+
+cudaError_t launch_merge(const double* scores, const long long* idx, int G, int B, int K, long long* out_idx,
+                         float* out_score, double* out_score64, cudaStream_t stream);
+
+cudaError_t launch_blend_normalize(const float* content, const float* collab, float alpha, const float* alpha_rows,
+                                   long long n, int d, float* out_f32, void* out_bf16, int d_pad,
+                                   cudaStream_t stream);
+cudaError_t launch_make_shadow(const float* table, long long n, int d, void* out_bf16, int d_pad, cudaStream_t stream);
+cudaError_t launch_norm_stats(const float* v, long long n, int d, float eps, double* out5, cudaStream_t stream);
+
+cudaError_t launch_pair_score(const float* table, long long n, int d, const long long* src, const long long* dst,
+                              long long P, float* out, cudaStream_t stream);
+
+cudaError_t launch_eval(const long long* topk, int U, int Kret, const long long* train_ptr,
+                        const long long* train_idx, const long long* val_ptr, const long long* val_idx,
+                        const float* val_rel, const int* cutoffs, int n_cut, long long n_items,
+                        double* per_user, unsigned int* seen_bitmap, cudaStream_t stream);
+cudaError_t launch_eval_reduce(const double* per_user, int U, int M, const long long* val_ptr,
+                               const unsigned int* seen_bitmap, long long n_items, int n_cut, double* out,
+                               cudaStream_t stream);
+
+}  // namespace hwer

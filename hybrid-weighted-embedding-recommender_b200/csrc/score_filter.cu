@@ -1,0 +1,387 @@
+// Fused score-and-select, stage 1: score a range of catalogue rows against a
+// resident block of queries on the tcgen05 tensor cores and admit only scores
+// at or above the per-query threshold into per-query candidate lists.  The
+// [items x queries] score matrix lives in TMEM only; it never reaches HBM.
+//
+// Replaces (together with select.cu) the exact k-NN search of the reference:
+//   hwer/recommendation_base.py:78-83  MultiKNN.query -> sklearn KDTree.query
+//   hwer/recommendation_base.py:171    find_closest_neighbours' candidate search
+// On unit-norm rows Euclidean order == dot-product order,
+// so the kernel scores raw dot products.
+//
+// Tile mapping (one CTA per SM, persistent):
+//   UMMA M = 128 catalogue rows  (A operand: TMA-streamed bf16 tiles, K-major, 128B swizzle)
+//   UMMA N = nq <= 256 queries   (B operand: resident in shared memory for the CTA's lifetime)
+//   UMMA K = 16, d_pad/16 steps  (accumulators: fp32 in TMEM, acc_stages-deep)
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..5 = epilogue (tcgen05.ld -> threshold compare -> rare append).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hwer {
+
+namespace {
+
+constexpr int kSlabBytes = kTileItems * 128;  // one 64-wide K block of an item tile: 16 KB
+constexpr int kThreadsTc = 192;
+
+__device__ __forceinline__ void append_candidate(unsigned long long* cand, unsigned int* cnt, unsigned int cap,
+                                                 int q, float s, uint32_t row) {
+    unsigned int slot = atomicAdd(&cnt[q], 1u);
+    if (slot < cap) cand[(size_t)q * cap + slot] = make_key(s, row);
+}
+
+// Compare W accumulator columns of one catalogue row against the thresholds of
+// the W queries they belong to; the hit path is rare and kept
+// out of line in 8-column groups.
+template <int W, bool DUMP>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const float* thr_s, int c0, int q_base,
+                                               long long row, bool row_ok, const FilterParams& p) {
+    if (DUMP) {
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                int q = q_base + c0 + j;
+                if (q < p.B) p.dump[(size_t)row * p.dump_ld + q] = __uint_as_float(v[j]);
+            }
+        }
+        return;
+    }
+    float t[W];
+    const float4* t4 = reinterpret_cast<const float4*>(thr_s + c0);
+#pragma unroll
+    for (int j = 0; j < W / 4; ++j) {
+        float4 x = t4[j];
+        t[4 * j + 0] = x.x; t[4 * j + 1] = x.y; t[4 * j + 2] = x.z; t[4 * j + 3] = x.w;
+    }
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < W; ++j) any |= (__uint_as_float(v[j]) >= t[j]);
+    if (any && row_ok) {
+#pragma unroll
+        for (int g = 0; g < W / 8; ++g) {
+            bool anyg = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) anyg |= (__uint_as_float(v[8 * g + j]) >= t[8 * g + j]);
+            if (anyg) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float s = __uint_as_float(v[8 * g + j]);
+                    if (s >= t[8 * g + j])
+                        append_candidate(p.cand, p.cnt, p.cap, q_base + c0 + 8 * g + j, s, (uint32_t)row);
+                }
+            }
+        }
+    }
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled operands need 1024-byte aligned slabs.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int nq = p.nq;
+    const int kb = p.kb;
+    const int q_slab = nq * 128;                 // bytes of one K block of the query operand
+    const int stage_bytes = kb * kSlabBytes;
+
+    uint8_t* q_smem = smem;
+    uint8_t* item_smem = q_smem + kb * q_slab;   // kb*q_slab is a multiple of 1024 (nq % 8 == 0)
+    float* thr_s = reinterpret_cast<float*>(item_smem + (size_t)p.stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + kMaxNQ);
+    uint64_t* full_bar = bars;                            // [stages]   TMA -> MMA
+    uint64_t* empty_bar = bars + p.stages;                // [stages]   MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * p.stages;            // [acc]      MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + p.acc_stages;      // [acc]      epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + p.acc_stages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < p.acc_stages; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);   // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int slot = blockIdx.x % p.slots;
+    const int qb0 = blockIdx.x / p.slots;
+    const uint32_t idesc = umma_idesc_bf16_f32(kTileItems, (uint32_t)nq);
+    const uint64_t policy = p.stream_once ? l2_policy_evict_first() : l2_policy_evict_last();
+
+    // Pipeline positions persist across query blocks.
+    uint32_t stage = 0, phase = 0;        // smem ring (producer and MMA each keep a copy)
+    uint32_t acc = 0, acc_phase = 0;      // TMEM ring (MMA and epilogue each keep a copy)
+
+    for (int qb = qb0; qb < p.nqb; qb += p.qb_step) {
+        const int q_base = qb * nq;
+        // ---- stage the query block: fp32 -> bf16 (RN), K-major, 128B swizzle ----
+        {
+            const int chunks_per_row = kb * 8;   // 16-byte chunks (8 bf16) per query row
+            for (int i = threadIdx.x; i < nq * chunks_per_row; i += kThreadsTc) {
+                const int r = i / chunks_per_row;
+                const int c = i - r * chunks_per_row;
+                const int q = q_base + r;
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c * 8 + j;
+                    f[j] = (q < p.B && col < p.d) ? __ldg(p.queries + (size_t)q * p.d + col) : 0.0f;
+                }
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[2], f[3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[6], f[7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                const int kblk = c >> 3;
+                const int cc = (c & 7) ^ (r & 7);
+                *reinterpret_cast<uint4*>(q_smem + (size_t)kblk * q_slab + r * 128 + cc * 16) = pk;
+            }
+            for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
+                const int q = q_base + i;
+                thr_s[i] = (q < p.B) ? p.thr[q] : __int_as_float(0x7f800000);
+            }
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+        }
+        __syncthreads();
+
+        if (warp == 0) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                    uint8_t* dst = item_smem + (size_t)stage * stage_bytes;
+                    const int tile_row = (int)(((long long)t * p.tile_mul) % p.tile_mod) * kTileItems;
+                    for (int k = 0; k < kb; ++k)
+                        tma_load_2d(dst + k * kSlabBytes, &tmap, k * kKBlock, tile_row, &full_bar[stage], policy);
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            if (lane == 0) {
+                const uint32_t q_addr = smem_u32(q_smem);
+                const uint32_t i_addr = smem_u32(item_smem);
+                for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + acc * (uint32_t)nq;
+                    const uint32_t a_base = i_addr + stage * (uint32_t)stage_bytes;
+                    for (int k = 0; k < kb; ++k) {
+#pragma unroll
+                        for (int s = 0; s < kKBlock / 16; ++s) {
+                            const uint64_t adesc = umma_desc_k_sw128(a_base + k * kSlabBytes + s * 32);
+                            const uint64_t bdesc = umma_desc_k_sw128(q_addr + k * q_slab + s * 32);
+                            umma_bf16(d_tmem, adesc, bdesc, idesc, (k | s) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
+                    umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+                    if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===================== epilogue (4 warps) =====================
+            const uint32_t quad = (uint32_t)warp & 3u;   // TMEM lane quadrant this warp may read
+            for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after_sync();
+                const long long row = (((long long)t * p.tile_mul) % p.tile_mod) * kTileItems + quad * 32 + lane;
+                const bool row_ok = row < p.n_items;
+                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * (uint32_t)nq;
+                int c0 = 0;
+                for (; c0 + 32 <= nq; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    epilogue_chunk<32, DUMP>(v, thr_s, c0, q_base, row, row_ok, p);
+                }
+                if (c0 < nq) {
+                    uint32_t v[16];
+                    tmem_ld_x16(taddr + c0, v);
+                    tmem_ld_wait();
+                    epilogue_chunk<16, DUMP>(v, thr_s, c0, q_base, row, row_ok, p);
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        // All MMAs reading this query block have retired once every epilogue warp is here.
+        __syncthreads();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------
+// Generic CUDA-core filter over the fp32 table (any d).  One thread per
+// catalogue row, queries staged through shared memory eight at a time.
+// ----------------------------------------------------------------------------
+constexpr int kSimtQ = 8;
+constexpr int kSimtThreads = 256;
+
+__global__ void __launch_bounds__(kSimtThreads)
+score_filter_simt_kernel(const float* __restrict__ table, long long n_items, int d, const float* __restrict__ queries,
+                         int B, const float* __restrict__ thr, unsigned long long* cand, unsigned int* cnt,
+                         unsigned int cap, long long row_begin, long long row_end) {
+    extern __shared__ float qs[];   // [kSimtQ][d]
+    __shared__ float ts[kSimtQ];
+    for (long long base = row_begin + (long long)blockIdx.x * kSimtThreads; base < row_end;
+         base += (long long)gridDim.x * kSimtThreads) {
+        const long long row = base + threadIdx.x;
+        const bool ok = row < row_end && row < n_items;
+        const float* x = table + (size_t)(ok ? row : row_begin) * d;
+        for (int q0 = 0; q0 < B; q0 += kSimtQ) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < kSimtQ * d; i += kSimtThreads) {
+                const int q = q0 + i / d;
+                qs[i] = (q < B) ? queries[(size_t)q * d + (i % d)] : 0.0f;
+            }
+            if (threadIdx.x < kSimtQ)
+                ts[threadIdx.x] = (q0 + threadIdx.x < B) ? thr[q0 + threadIdx.x] : __int_as_float(0x7f800000);
+            __syncthreads();
+            float acc[kSimtQ];
+#pragma unroll
+            for (int j = 0; j < kSimtQ; ++j) acc[j] = 0.0f;
+            for (int c = 0; c < d; ++c) {
+                const float xv = __ldg(x + c);
+#pragma unroll
+                for (int j = 0; j < kSimtQ; ++j) acc[j] = fmaf(xv, qs[j * d + c], acc[j]);
+            }
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < kSimtQ; ++j)
+                    if (acc[j] >= ts[j]) append_candidate(cand, cnt, cap, q0 + j, acc[j], (uint32_t)row);
+            }
+        }
+    }
+}
+
+__global__ void query_margin_kernel(const float* __restrict__ queries, int B, int d, float factor,
+                                    float* __restrict__ margin) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= B) return;
+    float s = 0.0f;
+    for (int c = lane_id(); c < d; c += 32) {
+        const float v = queries[(size_t)q * d + c];
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    // round the norm up a little: the bound must never be under-estimated
+    if (lane_id() == 0) margin[q] = factor * sqrtf(s) * 1.0001f;
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+size_t filter_tc_smem_bytes(int nq, int kb, int stages) {
+    return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + kMaxNQ * sizeof(float) +
+           (2 * stages + 8) * sizeof(uint64_t) + 16;
+}
+
+int filter_tc_pick_stages(int nq, int kb) {
+    int stages = 8;
+    while (stages > 0 && filter_tc_smem_bytes(nq, kb, stages) > (size_t)kSmemBudget) --stages;
+    return stages;
+}
+
+cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sms, cudaStream_t stream) {
+    if (p.tile_end <= p.tile_begin || p.B <= 0) return cudaSuccess;
+    p.stages = filter_tc_pick_stages(p.nq, p.kb);
+    if (p.stages < 2) return cudaErrorInvalidConfiguration;
+    p.acc_stages = 512 / p.nq;
+    if (p.acc_stages > 4) p.acc_stages = 4;
+    int cols = p.acc_stages * p.nq, pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    p.tmem_cols = pow2;
+    const int ntiles = p.tile_end - p.tile_begin;
+    int grid;
+    if (p.nqb <= num_sms) {
+        p.slots = num_sms / p.nqb;
+        if (p.slots > ntiles) p.slots = ntiles;
+        p.qb_step = p.nqb;
+        grid = p.slots * p.nqb;
+    } else {
+        p.slots = 1;
+        p.qb_step = num_sms;
+        grid = num_sms;
+    }
+    p.stream_once = (p.nqb == 1) ? 1 : 0;
+    const size_t smem = filter_tc_smem_bytes(p.nq, p.kb, p.stages);
+    cudaError_t e;
+    if (p.dump) {
+        e = cudaFuncSetAttribute(score_filter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        score_filter_tc_kernel<true><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
+    } else {
+        e = cudaFuncSetAttribute(score_filter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        score_filter_tc_kernel<false><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter_simt(const float* table, long long n_items, int d, const float* queries, int B,
+                               const float* thr, unsigned long long* cand, unsigned int* cnt, unsigned int cap,
+                               long long row_begin, long long row_end, int num_sms, cudaStream_t stream) {
+    if (row_end <= row_begin || B <= 0) return cudaSuccess;
+    long long blocks = (row_end - row_begin + kSimtThreads - 1) / kSimtThreads;
+    long long maxb = (long long)num_sms * 8;
+    int grid = (int)(blocks < maxb ? blocks : maxb);
+    size_t smem = (size_t)kSimtQ * d * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(score_filter_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+    if (e != cudaSuccess) return e;
+    score_filter_simt_kernel<<<grid, kSimtThreads, smem, stream>>>(table, n_items, d, queries, B, thr, cand, cnt, cap,
+                                                                   row_begin, row_end);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float* margin,
+                                cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, margin);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+}  // namespace hwer

@@ -1,0 +1,224 @@
+"""Tensor-level operators of the serving hot path.
+
+Each function hands raw device pointers of torch CUDA tensors to the C ABI (include/hwer_b200.h) on torch's
+current stream.  torch supplies memory and streams only; every computation below runs in libhwer_b200.so.
+There is deliberately no CPU implementation: CPU tensors are rejected.
+"""
+import ctypes
+from ctypes import c_uint32, c_void_p
+
+import torch
+
+from . import _native as N
+
+
+def _dev_ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: hwer_b200 has no CPU path" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must be %d-dimensional" % (name, ndim))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous (row-major)" % name)
+    return t
+
+
+def shadow_width(d):
+    return (int(d) + 63) // 64 * 64
+
+
+def blend_normalize(content, collab, alpha=0.5, want_shadow=True):
+    """V = unit(alpha * unit(content) + (1 - alpha) * unit(collab)) row-wise (the blend slot of
+    GcnNCF.prepare_for_knn, hwer/gcn_ncf.py:447-456; alpha = 0 or content=None is the reference's behaviour).
+    `alpha` is a float or an [N] fp32 CUDA tensor (per-row alpha).  Returns (fp32 table, bf16 shadow | None)."""
+    collab = _need(collab, torch.float32, "collab", 2)
+    n, d = collab.shape
+    if content is not None:
+        content = _need(content, torch.float32, "content", 2)
+        if tuple(content.shape) != (n, d):
+            raise ValueError("content %s and collaborative %s tables must have the same shape"
+                             % (tuple(content.shape), (n, d)))
+    alpha_rows = None
+    a = 0.0
+    if isinstance(alpha, torch.Tensor):
+        alpha_rows = _need(alpha, torch.float32, "alpha", 1)
+        if alpha_rows.shape[0] != n:
+            raise ValueError("per-row alpha must have one entry per row")
+    else:
+        a = float(alpha)
+    out = torch.empty_like(collab)
+    d_pad = shadow_width(d)
+    shadow = torch.empty((n, d_pad), dtype=torch.bfloat16, device=collab.device) if want_shadow else None
+    with torch.cuda.device(collab.device):
+        N.check(N.lib().hwer_blend_normalize(_dev_ptr(content), _dev_ptr(collab), a, _dev_ptr(alpha_rows), n, d,
+                                             _dev_ptr(out), _dev_ptr(shadow), d_pad, _stream(collab.device)))
+    return out, shadow
+
+
+def unit_length(a):
+    """hwer/utils.py:43-44 with axis=1 on a CUDA table."""
+    return blend_normalize(None, a, 0.0, want_shadow=False)[0]
+
+
+def make_shadow(table):
+    table = _need(table, torch.float32, "table", 2)
+    n, d = table.shape
+    d_pad = shadow_width(d)
+    shadow = torch.empty((n, d_pad), dtype=torch.bfloat16, device=table.device)
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_make_shadow(_dev_ptr(table), n, d, _dev_ptr(shadow), d_pad, _stream(table.device)))
+    return shadow
+
+
+def norm_stats(table, epsilon=1e-4):
+    """(violations, mean |norm-1|, positive, negative, max_norm) -- hwer/utils.py:51-57 plus the max norm."""
+    table = _need(table, torch.float32, "table", 2)
+    out = torch.empty(5, dtype=torch.float64, device=table.device)
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_norm_stats(_dev_ptr(table), table.shape[0], table.shape[1], float(epsilon),
+                                        _dev_ptr(out), _stream(table.device)))
+    v = out.cpu().tolist()
+    return int(v[0]), v[1], int(v[2]), int(v[3]), v[4]
+
+
+class TopKIndex:
+    """Exact top-k index over one [N, d] unit-norm fp32 table (one node type's rows): the replacement for a
+    per-type `KDTree(vectors[rows], leaf_size=128)` of MultiKNN (hwer/recommendation_base.py:65-76)."""
+
+    def __init__(self, table, shadow=None, max_norm=None):
+        self.table = _need(table, torch.float32, "table", 2)
+        self.n, self.d = self.table.shape
+        self.device = self.table.device
+        if shadow is None and shadow_width(self.d) <= 256:
+            shadow = make_shadow(self.table)
+        if shadow is not None:
+            shadow = _need(shadow, torch.bfloat16, "shadow", 2)
+            if shadow.shape[0] != self.n:
+                raise ValueError("shadow and table row counts differ")
+        self.shadow = shadow
+        if max_norm is None:
+            max_norm = norm_stats(self.table)[4]
+        self.max_norm = float(max_norm)
+        handle = c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_index_create(ctypes.byref(handle), _dev_ptr(self.table), _dev_ptr(shadow), self.n,
+                                              self.d, shadow.shape[1] if shadow is not None else 0, self.max_norm,
+                                              self.device.index if self.device.index is not None else
+                                              torch.cuda.current_device()))
+        self._h = handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                N.lib().hwer_index_destroy(h)
+            except Exception:
+                pass
+
+    def topk_async(self, queries, k, mode="exact", idx_offset=0, cap=0, out=None, want_f64=False):
+        """Enqueues the search on the current stream; results are valid after `finish()`."""
+        queries = _need(queries, torch.float32, "queries", 2)
+        if queries.shape[1] != self.d:
+            raise ValueError("query width %d != table width %d" % (queries.shape[1], self.d))
+        B = queries.shape[0]
+        k = int(k)
+        if k > self.n:
+            # sklearn: "k must be less than or equal to the number of training points"
+            raise ValueError("k=%d must be less than or equal to the number of rows %d" % (k, self.n))
+        if out is None:
+            idx = torch.empty((B, k), dtype=torch.int64, device=self.device)
+            score = torch.empty((B, k), dtype=torch.float32, device=self.device)
+            s64 = torch.empty((B, k), dtype=torch.float64, device=self.device) if want_f64 else None
+        else:
+            idx, score, s64 = out
+        m = N.MODE_EXACT if mode == "exact" else N.MODE_BF16 if mode == "bf16" else None
+        if m is None:
+            raise ValueError("mode must be 'exact' or 'bf16'")
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_topk(self._h, _dev_ptr(queries), B, k, m, int(cap), int(idx_offset), _dev_ptr(idx),
+                                      _dev_ptr(score), _dev_ptr(s64), _stream(self.device)))
+        return idx, score, s64
+
+    def finish(self):
+        need = c_uint32(0)
+        with torch.cuda.device(self.device):
+            rc = N.lib().hwer_topk_finish(self._h, _stream(self.device), ctypes.byref(need))
+        return rc, int(need.value)
+
+    def topk(self, queries, k, mode="exact", idx_offset=0, want_f64=False):
+        """Synchronous search with automatic retry when the candidate lists overflow (heavily tied data)."""
+        cap = 0
+        for _ in range(6):
+            idx, score, s64 = self.topk_async(queries, k, mode, idx_offset, cap, want_f64=want_f64)
+            rc, need = self.finish()
+            if rc == N.HWER_OK:
+                return (idx, score, s64) if want_f64 else (idx, score)
+            if rc != N.HWER_E_OVERFLOW:
+                N.check(rc)
+            cap = need
+        N.check(rc)
+
+    def debug_scores(self, queries):
+        queries = _need(queries, torch.float32, "queries", 2)
+        out = torch.zeros((self.n, queries.shape[0]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_debug_scores(self._h, _dev_ptr(queries), queries.shape[0], _dev_ptr(out),
+                                              queries.shape[0], _stream(self.device)))
+        return out
+
+
+def merge_topk(scores64, idx, want_f64=False):
+    """[G, B, k] per-shard results -> [B, k] under (score desc, row asc)."""
+    scores64 = _need(scores64, torch.float64, "scores64", 3)
+    idx = _need(idx, torch.int64, "idx", 3)
+    G, B, k = scores64.shape
+    o_idx = torch.empty((B, k), dtype=torch.int64, device=idx.device)
+    o_sc = torch.empty((B, k), dtype=torch.float32, device=idx.device)
+    o_s64 = torch.empty((B, k), dtype=torch.float64, device=idx.device) if want_f64 else None
+    with torch.cuda.device(idx.device):
+        N.check(N.lib().hwer_merge_topk(_dev_ptr(scores64), _dev_ptr(idx), G, B, k, _dev_ptr(o_idx), _dev_ptr(o_sc),
+                                        _dev_ptr(o_s64), _stream(idx.device)))
+    return (o_idx, o_sc, o_s64) if want_f64 else (o_idx, o_sc)
+
+
+def pair_score(table, src_rows, dst_rows):
+    """(dot + 1) / 2 of row pairs; row -1 = node unseen in training (hwer/recommendation_base.py:135-151)."""
+    table = _need(table, torch.float32, "table", 2)
+    src_rows = _need(src_rows, torch.int64, "src_rows", 1)
+    dst_rows = _need(dst_rows, torch.int64, "dst_rows", 1)
+    P = src_rows.shape[0]
+    out = torch.empty(P, dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_pair_score(_dev_ptr(table), table.shape[0], table.shape[1], _dev_ptr(src_rows),
+                                        _dev_ptr(dst_rows), P, _dev_ptr(out), _stream(table.device)))
+    return out
+
+
+def eval_metrics(topk_items, train_ptr, train_idx, val_ptr, val_idx, val_rel, cutoffs, n_items, per_user=False):
+    """Ranking metrics of hwer/validation.py:133-174 for all users at once; see include/hwer_b200.h for layouts."""
+    topk_items = _need(topk_items, torch.int64, "topk_items", 2)
+    dev = topk_items.device
+    U, kret = topk_items.shape
+    cut = torch.tensor(sorted(int(c) for c in cutoffs), dtype=torch.int32, device=dev)
+    if cut[-1].item() > 256 or cut[0].item() <= 0:
+        raise ValueError("cutoffs must lie in [1, 256]")
+    n_cut = cut.shape[0]
+    out = torch.empty(3 * n_cut + 3, dtype=torch.float64, device=dev)
+    pu = torch.empty((U, 3 * n_cut + 1), dtype=torch.float64, device=dev) if per_user else None
+    for nm, t in (("train_ptr", train_ptr), ("train_idx", train_idx), ("val_ptr", val_ptr), ("val_idx", val_idx)):
+        _need(t, torch.int64, nm, 1)
+    _need(val_rel, torch.float32, "val_rel", 1)
+    with torch.cuda.device(dev):
+        N.check(N.lib().hwer_eval_metrics(_dev_ptr(topk_items), U, kret, _dev_ptr(train_ptr), _dev_ptr(train_idx),
+                                          _dev_ptr(val_ptr), _dev_ptr(val_idx), _dev_ptr(val_rel), _dev_ptr(cut),
+                                          n_cut, int(n_items), _dev_ptr(out), _dev_ptr(pu), _stream(dev)))
+    return (out, pu) if per_user else out

@@ -1,0 +1,314 @@
+"""Host-side mirror of hwer/recommendation_base.py: the same classes, method names, argument meaning, return
+conventions and error behaviour, with every computation on the path delegated to the CUDA library.
+
+  Node, Edge                       hwer/recommendation_base.py:19-61
+  MultiKNN(nodes_to_idx, vectors)  :64-83   per-node-type exact index; query -> [(Node, euclidean dist)] ascending
+  RecommendationBase               :86-174  add_nodes / __build_knn__ / fit / predict / get_embeddings /
+                                            get_average_embeddings / find_closest_neighbours
+plus the entry points BASELINE.json's north_star names (`find_items_for_user`, `find_similar_items`: thin
+aliases over find_closest_neighbours) and batched, tensor-returning variants that avoid
+materialising Python tuples for large anchor sets.
+"""
+import abc
+import operator
+from collections import defaultdict
+from typing import Dict, List, Set, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .logging import getLogger
+from .utils import NodeNotFoundException
+
+NodeType = str
+NodeExternalId = Union[str, int]
+FeatureName = str
+
+
+class Node:
+    def __init__(self, node_type, node_external_id):
+        self.node_type = node_type
+        self.node_external_id = str(node_external_id)
+
+    def __key(self):
+        return (self.node_type, self.node_external_id)
+
+    def __hash__(self):
+        return hash(self.__key())
+
+    def __eq__(self, other):
+        if isinstance(other, Node):
+            return self.__key() == other.__key()
+        return NotImplemented
+
+    def __repr__(self):
+        return str(self.__key())
+
+
+class Edge:
+    def __init__(self, src: Node, dst: Node, weight: float):
+        self.src = src
+        self.dst = dst
+        self.weight = weight
+        self.contents = [src, dst, weight]
+
+    def __key(self):
+        return (self.src, self.dst, self.weight)
+
+    def __iter__(self):
+        return iter(self.contents)
+
+    def __hash__(self):
+        return hash(self.__key())
+
+    def __eq__(self, other):
+        if isinstance(other, Edge):
+            return self.__key() == other.__key()
+        return NotImplemented
+
+    def __repr__(self):
+        return "{src: %s, dst: %s, weight: %s}" % (self.src, self.dst, self.weight)
+
+
+class NodeIndex(dict):
+    """Node -> global row, with the `.inverse` view the reference gets from bidict (row -> Node)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._inverse = None
+
+    @property
+    def inverse(self):
+        if self._inverse is None or len(self._inverse) != len(self):
+            self._inverse = {v: k for k, v in self.items()}
+        return self._inverse
+
+    def __setitem__(self, key, value):
+        self._inverse = None
+        super().__setitem__(key, value)
+
+    def update(self, *a, **k):
+        self._inverse = None
+        super().update(*a, **k)
+
+
+def _as_device_table(vectors, device):
+    if isinstance(vectors, torch.Tensor):
+        t = vectors.to(device=device, dtype=torch.float32)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(device)
+    return t.contiguous()
+
+
+class MultiKNN:
+    def __init__(self, nodes_to_idx: Dict[Node, int], vectors, leaf_size=128, shadow=None, device=None,
+                 max_norm=None, mode="exact"):
+        # leaf_size is accepted for signature compatibility; there is no tree.
+        if not torch.cuda.is_available():
+            raise RuntimeError("hwer_b200 needs a CUDA device (B200): there is no CPU index")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nodes_to_idx = nodes_to_idx
+        self.mode = mode
+        assert len(nodes_to_idx) == len(vectors)
+        self.table = _as_device_table(vectors, self.device)
+        rows_by_type: Dict[str, List[int]] = defaultdict(list)
+        for n, i in nodes_to_idx.items():
+            rows_by_type[n.node_type].append(i)
+        self.idxs: Dict[str, np.ndarray] = {}
+        self.idxs_dev: Dict[str, torch.Tensor] = {}
+        self.offset: Dict[str, int] = {}
+        self.knn: Dict[str, ops.TopKIndex] = {}
+        self._tables = {}
+        for nt, rows in rows_by_type.items():
+            rows = np.asarray(rows, dtype=np.int64)
+            self.idxs[nt] = rows
+            self.idxs_dev[nt] = torch.from_numpy(rows).to(self.device)
+            contiguous = len(rows) > 0 and rows[0] + len(rows) - 1 == rows[-1] and np.all(np.diff(rows) == 1)
+            if contiguous:
+                # a row range of the shared table: no copy (the reference copies per type, :74)
+                sub = self.table[int(rows[0]):int(rows[0]) + len(rows)]
+                sh = shadow[int(rows[0]):int(rows[0]) + len(rows)] if shadow is not None else None
+                self.offset[nt] = int(rows[0])
+            else:
+                sub = self.table.index_select(0, self.idxs_dev[nt]).contiguous()
+                sh = shadow.index_select(0, self.idxs_dev[nt]).contiguous() if shadow is not None else None
+                self.offset[nt] = None
+            self._tables[nt] = sub
+            self.knn[nt] = ops.TopKIndex(sub, sh, max_norm=max_norm)
+
+    def _to_global(self, node_type, local_rows):
+        off = self.offset[node_type]
+        if off is not None:
+            return torch.where(local_rows >= 0, local_rows + off, local_rows)
+        g = self.idxs_dev[node_type][local_rows.clamp(min=0)]
+        return torch.where(local_rows >= 0, g, local_rows)
+
+    def query_batch(self, embeddings, node_type, k=200, mode=None, want_f64=False):
+        """[B, d] query embeddings -> (global rows [B, k] int64, dot products [B, k] fp32[, fp64]) on the device,
+        ordered (score descending, row ascending)."""
+        q = _as_device_table(embeddings, self.device)
+        if q.dim() == 1:
+            q = q[None, :]
+        res = self.knn[node_type].topk(q, k, mode or self.mode, want_f64=want_f64)
+        rows = self._to_global(node_type, res[0])
+        return (rows,) + tuple(res[1:])
+
+    def query(self, embedding, node_type, k=200) -> List[Tuple[Node, float]]:
+        """hwer/recommendation_base.py:78-83: k nearest rows of `node_type` by Euclidean distance, ascending."""
+        q = _as_device_table(embedding, self.device).reshape(1, -1)
+        rows, _ = self.query_batch(q, node_type, k=k)
+        rows = rows[0]
+        # Euclidean distance of the (fp32) rows to the embedding, in float64 like KDTree64
+        dist = (self.table.index_select(0, rows).double() - q.double()).norm(dim=1)
+        inv = self.nodes_to_idx.inverse
+        results = [(inv[i], dt) for i, dt in zip(rows.cpu().tolist(), dist.cpu().tolist())]
+        return list(sorted(results, key=operator.itemgetter(1), reverse=False))
+
+
+class RecommendationBase(metaclass=abc.ABCMeta):
+    def __init__(self, node_types: Set[str], n_dims: int = 32, device=None, mode: str = "exact"):
+        self.node_types: Set[NodeType] = node_types
+        self.nodes_to_idx: NodeIndex = NodeIndex()
+        self.knn: MultiKNN = None
+        self.vectors = None            # what __build_knn__ was given (numpy in the reference)
+        self.device_vectors = None     # the resident fp32 table the kernels read
+        self.fit_done = False
+        self.n_dims = n_dims
+        self.device = device
+        self.mode = mode               # "exact" (fp64-rescored, the reference's result) or "bf16"
+        self.log = getLogger(type(self).__name__)
+
+    def add_nodes(self, nodes: List[Node]):
+        assert len(set(nodes)) == len(nodes)
+        assert self.nodes_to_idx.keys().isdisjoint(set(nodes))
+        assert len(set([n.node_type for n in nodes]) - self.node_types) == 0
+        all_count = len(self.nodes_to_idx)
+        self.nodes_to_idx.update(zip(nodes, range(all_count, all_count + len(nodes))))
+        return self
+
+    def __build_knn__(self, vectors, shadow=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("hwer_b200 needs a CUDA device (B200): there is no CPU index")
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        table = _as_device_table(vectors, dev)
+        v, _, _, _, max_norm = ops.norm_stats(table)
+        assert v == 0
+        self.knn = MultiKNN(self.nodes_to_idx, table, leaf_size=128, shadow=shadow, device=dev, max_norm=max_norm,
+                            mode=self.mode)
+        self.vectors = vectors
+        self.device_vectors = self.knn.table
+        return self
+
+    @abc.abstractmethod
+    def fit(self, nodes: List[Node], edges: List[Edge], node_data: Dict[Node, Dict[FeatureName, object]], **kwargs):
+        assert not self.fit_done
+        edge_node_types = set([node.node_type for e in edges for node in [e.src, e.dst]])
+        sparsity = 1 - len(edges) / (len(nodes) * len(nodes))
+        self.log.info("Start Fitting Base Recommender with nodes = %s, edges = %s, sparsity = %s",
+                      len(nodes), len(edges), sparsity)
+        assert edge_node_types == self.node_types
+        assert len(set([i for e in edges for i in [e.src, e.dst]]) - set(nodes)) == 0
+        assert len(set(nodes)) == len(nodes)
+        assert len(set([n.node_type for n in nodes]) - self.node_types) == 0
+        self.add_nodes(nodes)
+        self.log.info("End Fitting Base Recommender")
+        return edges
+
+    # ------------------------------------------------------------------ pair scores
+    def _rows_of(self, nodes) -> torch.Tensor:
+        idx = [self.nodes_to_idx[n] if n in self.nodes_to_idx else -1 for n in nodes]
+        return torch.tensor(idx, dtype=torch.int64, device=self.device_vectors.device)
+
+    def predict_rows(self, src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
+        return ops.pair_score(self.device_vectors, src_rows, dst_rows)
+
+    def predict(self, node_pairs: List[Tuple[Node, Node]]) -> List[float]:
+        """Probability-like link score (dot + 1) / 2 for each pair; unknown nodes score ~0.5 (:135-151)."""
+        src, dst = zip(*node_pairs)
+        return self.predict_rows(self._rows_of(src), self._rows_of(dst)).cpu().numpy()
+
+    def get_embeddings(self, nodes: List[Node]):
+        rows = self._rows_of(nodes)
+        emb = self.device_vectors.index_select(0, rows.clamp(min=0))
+        mask = rows < 0
+        if bool(mask.any()):
+            emb[mask] = emb[mask].clamp(1e-6, 1e-5)
+        return emb.cpu().numpy()
+
+    def get_average_embeddings(self, entities: List[Node]):
+        rows = self._rows_of(entities)
+        return self._average_embedding(rows).cpu().numpy()
+
+    def _average_embedding(self, rows: torch.Tensor) -> torch.Tensor:
+        emb = self.device_vectors.index_select(0, rows.clamp(min=0))
+        mask = rows < 0
+        if bool(mask.any()):
+            emb[mask] = emb[mask].clamp(1e-6, 1e-5)
+        return ops.unit_length(emb.mean(dim=0, keepdim=True))[0]
+
+    def _query_embedding(self, anchor, positive=None, negative=None) -> torch.Tensor:
+        embedding_list = [self._average_embedding(self._rows_of([anchor]))]          # :164
+        if positive is not None and len(positive) > 0:
+            embedding_list.append(self._average_embedding(self._rows_of(positive)))  # :165-166
+        if negative is not None and len(negative) > 0:
+            embedding_list.append(-1 * self._average_embedding(self._rows_of(negative)))   # :167-168
+        return torch.stack(embedding_list).mean(dim=0)                                # :170 (not re-normalised)
+
+    # ------------------------------------------------------------------ retrieval
+    def _check_query(self, node_type, anchor):
+        assert self.fit_done
+        assert node_type in self.node_types and node_type in self.knn.knn
+        if anchor not in self.nodes_to_idx:
+            raise NodeNotFoundException("Node = %s, was not provided in training" % anchor)
+
+    def find_closest_neighbours(self, node_type: str, anchor: Node, positive: List[Node] = None,
+                                negative: List[Node] = None, k=200) -> List[Tuple[Node, float]]:
+        self._check_query(node_type, anchor)
+        embedding = self._query_embedding(anchor, positive, negative)
+        rows, _ = self.knn.query_batch(embedding[None, :], node_type, k=k)
+        rows = rows[0]
+        anchor_rows = torch.full_like(rows, self.nodes_to_idx[anchor])
+        scores = self.predict_rows(anchor_rows, rows).cpu().tolist()                  # :172
+        inv = self.nodes_to_idx.inverse
+        nodes = [inv[i] for i in rows.cpu().tolist()]
+        return list(sorted(zip(nodes, scores), key=operator.itemgetter(1), reverse=True))   # :173
+
+    def find_items_for_user(self, user: Node, k=200, positive: List[Node] = None, negative: List[Node] = None,
+                            node_type: str = "item") -> List[Tuple[Node, float]]:
+        """north_star name for find_closest_neighbours(node_type='item', anchor=<user>)."""
+        return self.find_closest_neighbours(node_type, user, positive, negative, k)
+
+    def find_similar_items(self, item: Node, k=200, positive: List[Node] = None, negative: List[Node] = None
+                           ) -> List[Tuple[Node, float]]:
+        """north_star name for find_closest_neighbours(node_type=<item's type>, anchor=<item>); like the
+        reference, the anchor itself is returned first."""
+        return self.find_closest_neighbours(item.node_type, item, positive, negative, k)
+
+    def _batch_scores(self, anchor_rows, rows, dots):
+        """Final score convention of the base class: (anchor . node + 1) / 2, each row sorted descending."""
+        B, k = rows.shape
+        s = self.predict_rows(anchor_rows[:, None].expand(B, k).reshape(-1).contiguous(),
+                              rows.reshape(-1).contiguous()).reshape(B, k)
+        s = torch.where(rows >= 0, s, torch.full_like(s, float("-inf")))
+        s, order = torch.sort(s, dim=1, descending=True, stable=True)
+        return torch.gather(rows, 1, order), s
+
+    def find_closest_neighbours_batch(self, node_type: str, anchors: List[Node], k=200
+                                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One search for all anchors (the loop of validation.model_get_topk_knn, hwer/validation.py:30-35).
+        Returns device tensors (global rows [B, k], scores [B, k]) in the same order and score convention as
+        find_closest_neighbours(node_type, anchor, k=k) called per anchor."""
+        assert self.fit_done
+        assert node_type in self.node_types and node_type in self.knn.knn
+        for a in anchors:
+            if a not in self.nodes_to_idx:
+                raise NodeNotFoundException("Node = %s, was not provided in training" % a)
+        anchor_rows = self._rows_of(anchors)
+        queries = ops.unit_length(self.device_vectors.index_select(0, anchor_rows))
+        rows, dots = self.knn.query_batch(queries, node_type, k=k)
+        return self._batch_scores(anchor_rows, rows, dots)
+
+    def rows_to_nodes(self, rows: torch.Tensor, scores: torch.Tensor) -> List[List[Tuple[Node, float]]]:
+        inv = self.nodes_to_idx.inverse
+        return [[(inv[i], s) for i, s in zip(r, sc) if i >= 0] for r, sc in zip(rows.cpu().tolist(), scores.cpu().tolist())]

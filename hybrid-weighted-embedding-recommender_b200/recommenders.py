@@ -1,0 +1,106 @@
+"""Serving-side mirrors of the reference's two recommenders.
+
+The reference classes train their tables inside fit() (feature encoders + PCA for ContentRecommendation,
+DGL GraphSAGE + optional NCF for GcnNCF); training is out of scope here.  These
+classes take the trained [N, d] tables as fit() keyword arguments and reproduce everything from the blend slot
+onwards:
+
+  ContentRecommendation.fit tail      hwer/content_recommender.py:94-97   (__build_knn__, fit_done, return table)
+  GcnNCF.prepare_for_knn              hwer/gcn_ncf.py:447-456             (+ the north_star alpha blend)
+  GcnNCF.fit tail                     hwer/gcn_ncf.py:439-445
+  GcnNCF.predict (cosine branch)      hwer/gcn_ncf.py:330-334
+  GcnNCF.find_closest_neighbours      hwer/gcn_ncf.py:363-383             score = (2 - euclidean distance) / 2
+"""
+import operator
+from typing import Dict, List, Set, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .recommendation_base import Edge, FeatureName, Node, RecommendationBase, _as_device_table
+
+
+class ContentRecommendation(RecommendationBase):
+    def __init__(self, embedding_mapper=None, node_types: Set[str] = None, n_dims: int = 32, device=None,
+                 mode: str = "exact"):
+        super().__init__(node_types, n_dims, device=device, mode=mode)
+        self.embedding_mapper = embedding_mapper
+
+    def fit(self, nodes: List[Node], edges: List[Edge], node_data: Dict[Node, Dict[FeatureName, object]] = None,
+            vectors=None, **kwargs):
+        """`vectors`: the finished [N, n_dims] unit-norm content table (what __build_content_embeddings__
+        produces in the reference), row i belonging to nodes[i]."""
+        if vectors is None:
+            raise ValueError("hwer_b200 serves trained tables: pass vectors=<[N, d] unit-norm array>")
+        super().fit(nodes, edges, node_data, **kwargs)
+        self.__build_knn__(vectors)
+        self.fit_done = True
+        return self.vectors
+
+
+class GcnNCF(RecommendationBase):
+    def __init__(self, embedding_mapper=None, node_types: Set[str] = None, n_dims: int = 32, alpha: float = 0.0,
+                 device=None, mode: str = "exact"):
+        super().__init__(node_types, n_dims, device=device, mode=mode)
+        assert n_dims % 2 == 0
+        self.embedding_mapper = embedding_mapper
+        self.alpha = alpha            # weight of the content table in the blend; 0.0 = the reference's behaviour
+        self.ncf_enabled = False      # the NCF re-rank (gcn_ncf.py:336-361,384-386) is not built yet
+        self.shadow = None
+
+    def prepare_for_knn(self, content_vectors, collaborative_vectors, alpha=None):
+        """unit(alpha * unit(content) + (1 - alpha) * unit(collaborative)) on the device; numpy in -> numpy out."""
+        if collaborative_vectors.shape[1] > self.n_dims:
+            # the reference reduces with sklearn PCA here (gcn_ncf.py:449-452): an offline step, not served
+            raise ValueError("collaborative table is wider than n_dims; reduce it offline (PCA) first")
+        elif collaborative_vectors.shape[1] < self.n_dims:
+            raise ValueError()
+        alpha = self.alpha if alpha is None else alpha
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        g = _as_device_table(collaborative_vectors, dev)
+        use_content = content_vectors is not None and not (isinstance(alpha, float) and alpha == 0.0)
+        c = None
+        if use_content:
+            if content_vectors.shape != collaborative_vectors.shape:
+                raise ValueError("content and collaborative tables must have the same shape to be blended")
+            c = _as_device_table(content_vectors, dev)
+        if isinstance(alpha, np.ndarray):
+            alpha = torch.from_numpy(alpha.astype(np.float32)).to(dev)
+        table, self.shadow = ops.blend_normalize(c, g, alpha if use_content else 0.0)
+        self._device_table = table
+        if isinstance(collaborative_vectors, torch.Tensor):
+            return table
+        return table.cpu().numpy()
+
+    def fit(self, nodes: List[Node], edges: List[Edge], node_data: Dict[Node, Dict[FeatureName, object]] = None,
+            content_vectors=None, collaborative_vectors=None, alpha=None, **kwargs):
+        if collaborative_vectors is None:
+            raise ValueError("hwer_b200 serves trained tables: pass collaborative_vectors=<[N, d] array>")
+        super().fit(nodes, edges, node_data, **kwargs)
+        knn_vectors = self.prepare_for_knn(content_vectors, collaborative_vectors, alpha)
+        # hand the device-resident table and its bf16 shadow straight to the index (no second upload)
+        RecommendationBase.__build_knn__(self, self._device_table, shadow=self.shadow)
+        self.vectors = knn_vectors
+        self.fit_done = True
+        return self.vectors
+
+    def find_closest_neighbours(self, node_type: str, anchor: Node, positive: List[Node] = None,
+                                negative: List[Node] = None, k=200) -> List[Tuple[Node, float]]:
+        self._check_query(node_type, anchor)
+        embedding = self._query_embedding(anchor, positive, negative)
+        node_dist_list = self.knn.query(embedding, node_type, k=k)
+        nodes, dist = zip(*node_dist_list)
+        dist = (-1 * np.array(dist) + 2) / 2                                          # gcn_ncf.py:381
+        return list(sorted(zip(nodes, dist), key=operator.itemgetter(1), reverse=True))
+
+    def _batch_scores(self, anchor_rows, rows, dots):
+        # (2 - ||q - x||) / 2 with q the unit anchor row: distance from the fp64 difference like KDTree64
+        B, k = rows.shape
+        q = ops.unit_length(self.device_vectors.index_select(0, anchor_rows)).double()
+        x = self.device_vectors.index_select(0, rows.clamp(min=0).reshape(-1)).reshape(B, k, -1).double()
+        dist = (x - q[:, None, :]).norm(dim=2)
+        s = ((2.0 - dist) / 2.0)
+        s = torch.where(rows >= 0, s, torch.full_like(s, float("-inf")))
+        s, order = torch.sort(s, dim=1, descending=True, stable=True)
+        return torch.gather(rows, 1, order), s

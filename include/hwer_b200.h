@@ -1,0 +1,125 @@
+/* hwer_b200.h -- C ABI of the B200-native serving hot path of
+ * faizanahemad/Hybrid-Weighted-Embedding-Recommender ("hwer").
+ *
+ * The reference is pure Python and has no FFI; the seams this library sits
+ * behind are the methods of hwer/recommendation_base.py and the helpers of
+ * hwer/utils.py / hwer/validation.py cited on each entry point below (paths are
+ * relative to the reference checkout).  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer named *_dev is a CUDA device pointer on the index's device;
+ *    every other pointer is host memory;
+ *  - tables are row-major, C-contiguous; `stream` is a cudaStream_t passed as
+ *    void* (NULL = the legacy default stream); calls only ENQUEUE work unless
+ *    stated otherwise;
+ *  - return value: 0 on success, a negative hwer_status otherwise;
+ *    hwer_last_error() returns a thread-local human-readable message;
+ *  - there is no CPU fallback: without a CUDA device of compute capability 10.x
+ *    every compute entry point fails with HWER_E_CUDA / HWER_E_ARCH.
+ */
+#ifndef HWER_B200_H
+#define HWER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum hwer_status {
+    HWER_OK = 0,
+    HWER_E_INVALID = -1,     /* bad argument (NULL, negative size, d_pad not a multiple of 64, ...)          */
+    HWER_E_CUDA = -2,        /* a CUDA runtime / driver call failed                                         */
+    HWER_E_ARCH = -3,        /* device is not sm_100 (B200)                                                 */
+    HWER_E_K_TOO_LARGE = -4, /* k > rows of the index: sklearn's KDTree.query raises ValueError here        */
+    HWER_E_OVERFLOW = -5,    /* candidate lists overflowed: re-run hwer_topk with cap >= *needed_cap        */
+    HWER_E_NOMEM = -6
+} hwer_status;
+
+#define HWER_MODE_EXACT 0 /* bf16 tensor-core filter with a proven margin + fp64 re-score from the fp32 table */
+#define HWER_MODE_BF16 1  /* bf16 tensor-core scores returned as they are                                    */
+
+typedef struct hwer_index hwer_index_t;
+
+const char* hwer_last_error(void);
+int hwer_version(void);
+
+/* Row width of the bf16 shadow table for logical width d (next multiple of 64). */
+int32_t hwer_shadow_width(int32_t d);
+
+/* V = unit(alpha * unit(C) + (1 - alpha) * unit(G)) row-wise; unit(a) = a / ||a||_2 without epsilon.
+ * Replaces: GcnNCF.prepare_for_knn, hwer/gcn_ncf.py:447-456 (the blend slot; the reference computes the
+ *           alpha = 0 case) and utils.unit_length, hwer/utils.py:43-44.
+ * content_dev may be NULL (plain unit_length of collab_dev); alpha_rows_dev (per-row alpha, [n]) may be NULL;
+ * out_bf16_dev (NULL to skip) receives the [n, d_pad] bf16 shadow with zero padding. */
+int hwer_blend_normalize(const float* content_dev, const float* collab_dev, float alpha,
+                         const float* alpha_rows_dev, int64_t n, int32_t d, float* out_f32_dev,
+                         void* out_bf16_dev, int32_t d_pad, void* stream);
+
+/* bf16 shadow (round-to-nearest-even, zero-padded to d_pad columns) of an already normalised fp32 table: the
+ * operand the tensor-core scorer streams when __build_knn__ (hwer/recommendation_base.py:105-110) is handed a
+ * finished table.  No reference counterpart (the reference's KDTree keeps a float64 copy instead, :74). */
+int hwer_make_shadow(const float* table_dev, int64_t n, int32_t d, void* out_bf16_dev, int32_t d_pad, void* stream);
+
+/* Row-norm statistics of an [n, d] fp32 table.
+ * Replaces: utils.unit_length_violations(a, axis=1, epsilon), hwer/utils.py:51-57, asserted by
+ *           RecommendationBase.__build_knn__, hwer/recommendation_base.py:105-107.
+ * out5_dev = {violations, mean |norm - 1|, positive violations, negative violations, max norm} (doubles). */
+int hwer_norm_stats(const float* table_dev, int64_t n, int32_t d, float epsilon, double* out5_dev, void* stream);
+
+/* Index over one node type's rows (the per-type KDTree of MultiKNN.__init__, hwer/recommendation_base.py:65-76).
+ * The fp32 table and its bf16 shadow are BORROWED: they must outlive the index.  max_norm is the largest row
+ * norm (from hwer_norm_stats); it scales the exact-mode admission margin. */
+int hwer_index_create(hwer_index_t** out, const float* table_f32_dev, const void* shadow_bf16_dev, int64_t n,
+                      int32_t d, int32_t d_pad, float max_norm, int32_t device);
+int hwer_index_destroy(hwer_index_t* index);
+
+/* Exact top-k by dot product of B queries against every row of the index.
+ * Replaces: MultiKNN.query, hwer/recommendation_base.py:78-83 (sklearn KDTree.query, exact Euclidean k-NN:
+ *           on unit rows the order equals descending dot product) for a whole batch of anchors, i.e. the loop
+ *           of validation.model_get_topk_knn, hwer/validation.py:30-35.
+ * queries_dev [B, d] fp32 (any norm).  Results are ordered (score descending, row ascending); rows are local to
+ * the index plus idx_offset; missing entries (fewer than k finite scores) are row -1 / score -inf.
+ * cap = per-query candidate-list capacity (0 = automatic).  out_score64_dev may be NULL.
+ * Asynchronous; call hwer_topk_finish before trusting the outputs. */
+int hwer_topk(hwer_index_t* index, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
+              int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev,
+              void* stream);
+/* Synchronises `stream` and reports candidate-list overflow of the topk calls enqueued since the last finish. */
+int hwer_topk_finish(hwer_index_t* index, void* stream, uint32_t* needed_cap);
+
+/* Debug/validation aid: the full bf16 tensor-core score matrix out[n, ld] (ld >= B) for small problems. */
+int hwer_debug_scores(hwer_index_t* index, const float* queries_dev, int32_t B, float* out_dev, int64_t ld,
+                      void* stream);
+
+/* G shards x [B, k] -> [B, k] under the same ordering rule (after the NCCL all-gather of per-GPU results).
+ * No reference counterpart (the reference is single-process); SURVEY.md section 8(e). */
+int hwer_merge_topk(const double* scores_dev, const int64_t* idx_dev, int32_t G, int32_t B, int32_t k,
+                    int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream);
+
+/* out[p] = (dot(row src[p], row dst[p]) + 1) / 2; a row id outside [0, n) means "node not seen in training"
+ * and scores with clip(row 0, 1e-6, 1e-5).
+ * Replaces: RecommendationBase.predict / get_embeddings, hwer/recommendation_base.py:135-151
+ *           (and GcnNCF.predict's cosine branch, hwer/gcn_ncf.py:330-334). */
+int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t* src_dev, const int64_t* dst_dev,
+                    int64_t P, float* out_dev, void* stream);
+
+/* Ranking metrics for U users in one pass.
+ * Replaces: the per-user loops of validation.extraction_efficiency, hwer/validation.py:133-174, with
+ *           utils.reciprocal_rank / ndcg / binary_ndcg / recall, hwer/utils.py:71-121.
+ * topk_dev [U, kret] item ids in rank order (-1 = none); train CSR rows sorted ascending by item id; validation
+ * CSR rows sorted by relevance descending (train items may be present, they are skipped).
+ * cutoffs_dev ascending, last <= 256.  out_dev has 3*n_cut + 3 doubles:
+ *   [3c] recall@c, [3c+1] graded ndcg@c, [3c+2] binary ndcg@c (means over users with a validation row),
+ *   [3*n_cut] MRR, [3*n_cut+1] distinct items among all users' filtered top-max_cut, [3*n_cut+2] #validation users.
+ * per_user_dev (NULL to skip) receives the [U, 3*n_cut+1] per-user values. */
+int hwer_eval_metrics(const int64_t* topk_dev, int32_t U, int32_t kret, const int64_t* train_ptr_dev,
+                      const int64_t* train_idx_dev, const int64_t* val_ptr_dev, const int64_t* val_idx_dev,
+                      const float* val_rel_dev, const int32_t* cutoffs_dev, int32_t n_cut, int64_t n_items,
+                      double* out_dev, double* per_user_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HWER_B200_H */

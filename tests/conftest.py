@@ -1,0 +1,68 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden_c1():
+    return np.load(os.path.join(GOLDEN, "reference_c1.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_eval():
+    return np.load(os.path.join(GOLDEN, "reference_eval.npz"))
+
+
+def synthetic_case(n_users, n_items, d, seed):
+    """Same generator as oracle/make_golden.py (legacy RandomState is stable across numpy versions)."""
+    rs = np.random.RandomState(seed)
+    content = rs.standard_normal((n_users + n_items, d)).astype(np.float32)
+    collab = rs.standard_normal((n_users + n_items, d)).astype(np.float32)
+    return content, collab
+
+
+def synthetic_edges(n_users, n_items, seed, val_per_user=3, min_train=5, max_train=40):
+    rs = np.random.RandomState(seed)
+    train, val = [], []
+    for u in range(n_users):
+        deg = rs.randint(min_train, max_train + 1)
+        items = rs.choice(n_items, size=deg + val_per_user, replace=False)
+        ratings = rs.randint(1, 6, size=deg + val_per_user)
+        for it, r in zip(items[:deg], ratings[:deg]):
+            train.append((u, int(it), float(r)))
+        if u % 7 != 0:
+            for it, r in zip(items[deg:], ratings[deg:]):
+                val.append((u, int(it), float(r)))
+            if u % 5 == 0:
+                val.append((u, int(items[0]), 5.0))
+    return train, val

@@ -1,0 +1,153 @@
+"""CPU: the oracle (oracle/hwer_oracle.py) against outputs of the REFERENCE ITSELF (tests/golden/*.npz, made by
+oracle/make_golden.py from /root/reference).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+import hwer_oracle as O
+from conftest import synthetic_case, synthetic_edges
+
+
+@pytest.fixture(scope="module")
+def c1(golden_c1):
+    n_users, n_items, d, k = [int(x) for x in golden_c1["shape"]]
+    content, collab = synthetic_case(n_users, n_items, d, seed=int(golden_c1["seed"][0]))
+    table = O.blend_normalize(content, collab, 0.0)        # alpha = 0 == reference prepare_for_knn
+    users = [O.Node("user", i) for i in range(n_users)]
+    items = [O.Node("item", i) for i in range(n_items)]
+    r = O.OracleRecommender({"user", "item"}, n_dims=d)
+    r.add_nodes(users + items)
+    r.build_knn(table)
+    return dict(g=golden_c1, table=table, users=users, items=items, rec=r, k=k, content=content, collab=collab)
+
+
+def test_table_matches_reference_prepare_for_knn(c1):
+    g, table = c1["g"], c1["table"]
+    assert table.dtype == np.float32
+    np.testing.assert_array_equal(table[[0, 1, 942, 943, 2624]], g["table_rows"])
+    assert abs(float(np.abs(table.astype(np.float64)).sum()) - float(g["table_checksum"][0])) < 1e-6
+
+
+def test_unit_length_violations(c1):
+    g, table = c1["g"], c1["table"]
+    np.testing.assert_allclose([float(x) for x in O.unit_length_violations(table, axis=1)], g["viol"], rtol=1e-12)
+    p = table.copy()
+    p[3] *= 1.01
+    p[10] *= 0.9
+    p[11] *= 1.0 + 5e-5
+    got = [float(x) for x in O.unit_length_violations(p, axis=1)]
+    np.testing.assert_allclose(got, g["viol_perturbed"], rtol=1e-12)
+    assert got[0] == 2 and got[2] == 1 and got[3] == 1
+
+
+def _ids(res):
+    return [int(n.node_external_id) for n, s in res], [float(s) for n, s in res]
+
+
+def test_find_items_for_user_matches_reference(c1):
+    g, r = c1["g"], c1["rec"]
+    for j, u in enumerate(g["user_anchors"]):
+        idx, sc = _ids(r.find_closest_neighbours("item", c1["users"][int(u)], k=c1["k"]))
+        assert idx == list(g["items_for_user_idx"][j])
+        np.testing.assert_allclose(sc, g["items_for_user_score"][j], rtol=0, atol=1e-7)
+
+
+def test_find_similar_items_matches_reference(c1):
+    g, r = c1["g"], c1["rec"]
+    for j, i in enumerate(g["item_anchors"]):
+        idx, sc = _ids(r.find_closest_neighbours("item", c1["items"][int(i)], k=c1["k"]))
+        assert idx == list(g["similar_items_idx"][j])
+        assert idx[0] == int(i)          # the anchor item itself comes back first
+        np.testing.assert_allclose(sc, g["similar_items_score"][j], rtol=0, atol=1e-7)
+
+
+def test_default_k_and_posneg_match_reference(c1):
+    g, r = c1["g"], c1["rec"]
+    users, items = c1["users"], c1["items"]
+    n_items = len(items)
+    for j, u in enumerate(g["user_anchors"][:8]):
+        idx, sc = _ids(r.find_closest_neighbours("user", users[int(u)]))      # default k = 200
+        assert len(idx) == 200 and idx == list(g["users_k200_idx"][j])
+    for j, u in enumerate(g["user_anchors"][:16]):
+        u = int(u)
+        pos = [items[(u * 3 + t) % n_items] for t in range(3)]
+        neg = [items[(u * 5 + t + 1) % n_items] for t in range(2)]
+        idx, sc = _ids(r.find_closest_neighbours("item", users[u], positive=pos, negative=neg, k=c1["k"]))
+        assert idx == list(g["posneg_idx"][j])
+        np.testing.assert_allclose(sc, g["posneg_score"][j], atol=1e-7)
+
+
+def test_gcn_score_convention_matches_reference(c1):
+    g = c1["g"]
+    r = O.OracleRecommender({"user", "item"}, n_dims=64, gcn_scores=True)
+    r.add_nodes(c1["users"] + c1["items"])
+    r.build_knn(c1["table"])
+    for j, u in enumerate(g["user_anchors"]):
+        idx, sc = _ids(r.find_closest_neighbours("item", c1["users"][int(u)], k=c1["k"]))
+        assert idx == list(g["gcn_items_for_user_idx"][j])
+        np.testing.assert_allclose(sc, g["gcn_items_for_user_score"][j], atol=1e-12)
+
+
+def test_predict_matches_reference_incl_unknown_nodes(c1):
+    g, r = c1["g"], c1["rec"]
+    nodes = c1["users"] + c1["items"]
+    pairs = []
+    for a, b in zip(g["pair_src"], g["pair_dst"]):
+        pairs.append((nodes[a] if a >= 0 else O.Node("user", "ghost%d" % len(pairs)),
+                      nodes[b] if b >= 0 else O.Node("item", "ghost%d" % len(pairs))))
+    np.testing.assert_allclose(r.predict(pairs), g["pair_pred"], atol=1e-7)
+    assert abs(g["pair_pred"][-1] - 0.5) < 1e-6          # unknown x unknown ~ 0.5
+
+
+def test_exact_topk_equals_reference_order(c1):
+    """Brute-force fp64 (score desc, row asc) == the reference's KD-tree retrieval on this table."""
+    g, table = c1["g"], c1["table"]
+    n_users = len(c1["users"])
+    q = O.unit_length(table[g["user_anchors"]], axis=1)
+    idx, sc = O.exact_topk(table[n_users:], q, c1["k"])
+    np.testing.assert_array_equal(idx, g["items_for_user_idx"])
+    np.testing.assert_allclose((sc + 1) / 2, g["items_for_user_score"], atol=1e-6)
+
+
+def test_unknown_anchor_and_k_too_large(c1):
+    r = c1["rec"]
+    with pytest.raises(O.NodeNotFoundException):
+        r.find_closest_neighbours("item", O.Node("user", "nobody"))
+    with pytest.raises(ValueError):
+        r.find_closest_neighbours("item", c1["users"][0], k=len(c1["items"]) + 1)
+
+
+def test_metric_spot_values(golden_eval):
+    y = {"a": 1, "b": 1, "c": 1}
+    got = [O.ndcg(y, ["x", "a", "b"]), O.recall(y, ["x", "a", "b"]), O.reciprocal_rank(["a"], ["x", "a"]),
+           O.binary_ndcg({"a": 5.0, "b": 2.0}, ["b", "q", "a"]),
+           O.ndcg({"s1": 5.0, "s2": 4.8, "s3": 3.0, "s4": 4.1, "s5": 2.9, "s6": 0.9}, ["s1", "s2", "s3", "s5", "s6"])]
+    np.testing.assert_allclose(got, golden_eval["spot"], rtol=1e-14)
+    assert abs(got[0] - 0.5307212714866815) < 1e-12      # SURVEY.md section 8c spot value
+
+
+def test_extraction_metrics_match_reference(golden_eval):
+    nu, ni, dd = [int(x) for x in golden_eval["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, seed=int(golden_eval["seeds"][0]))
+    table = O.unit_length(collab, axis=1)
+    users = [O.Node("user", i) for i in range(nu)]
+    items = [O.Node("item", i) for i in range(ni)]
+    m = O.OracleRecommender({"user", "item"}, n_dims=dd)
+    m.add_nodes(users + items)
+    m.build_knn(table)
+    tr, vl = synthetic_edges(nu, ni, seed=int(golden_eval["seeds"][1]))
+    train = [(users[u], items[i], w) for u, i, w in tr]
+    val = [(users[u], items[i], w) for u, i, w in vl]
+    all_users = list(set([u for u, i, r in train] + [u for u, i, r in val]))
+    preds = O.model_get_topk_knn(m, all_users, "item")
+    out = O.extraction_metrics(preds, train, val, "item")
+    ref = dict(zip([str(k) for k in golden_eval["metric_keys"]], golden_eval["metric_values"]))
+    for key in ("recall@100", "ndcg_b@100", "ndcg_b@10", "recall@10", "diversity"):
+        assert abs(out[key] - ref[key]) < 1e-12, key
+
+
+def test_compare_topk_tie_rule():
+    ref_idx = np.array([[5, 3, 9, 1]])
+    ref_sc = np.array([[0.9, 0.5, 0.5, 0.1]])
+    assert O.compare_topk(np.array([[5, 9, 3, 1]]), ref_sc, ref_idx, ref_sc) == 0     # swap inside a tie group
+    assert O.compare_topk(np.array([[3, 5, 9, 1]]), ref_sc, ref_idx, ref_sc) == 1     # real reordering
+    assert O.compare_topk(np.array([[5, 3, 9, 7]]), ref_sc, ref_idx, ref_sc) == 0     # tie straddling the cut
