@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the serving hot path on BASELINE.json's headline workload (config C4):
+exact top-100 by cosine over a synthetic 10M x 128 unit-norm catalogue, item-sharded over N GPUs.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one batch of `--batch` queries answered against the whole
+catalogue.  `value` = queries/s with queries and catalogue resident in HBM; `e2e` = the same through the public
+API with pinned-host queries copied in and results copied out every step.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "top-100 cosine queries/sec @10Mx128 items"
+UNIT = "queries/s"
+CHUNK = 1_000_000          # rows generated per seeded chunk: the table is the same for every shard count
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--items", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--mode", default="exact", choices=["exact", "bf16"])
+    ap.add_argument("--alpha", type=float, default=0.5)
+    ap.add_argument("--sweep", default="1,64", help="extra batch sizes reported under 'sweep' (N=1 only)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tc_burst=float(d["bf16_tflops"]),
+                    tc_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), basis="of measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, basis="of fallback")
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = "/tmp/hwer_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_table(rows, d, seed=0):
+    rs = np.random.RandomState(seed)
+    c = rs.standard_normal((rows, d)).astype(np.float32)
+    g = rs.standard_normal((rows, d)).astype(np.float32)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hwer_oracle as O
+    return O.blend_normalize(c, g, 0.5)
+
+
+def build_cpu_model(table, queries):
+    """The reference's index + anchors (restated in oracle/hwer_oracle.py): one KD-tree per node type."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hwer_oracle as O
+    users = [O.Node("user", i) for i in range(len(queries))]
+    items = [O.Node("item", i) for i in range(len(table))]
+    m = O.OracleRecommender({"user", "item"}, n_dims=table.shape[1])
+    m.add_nodes(users + items)
+    t0 = time.time()
+    m.build_knn(np.concatenate([queries, table]).astype(np.float32))
+    return m, users, time.time() - t0
+
+
+_CPU_MODEL = None      # set before forking so pool workers inherit the built trees instead of unpickling them
+
+
+def _cpu_loop(args):
+    model, anchors, k = args
+    if model is None:
+        model = _CPU_MODEL
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hwer_oracle as O
+    O.model_get_topk_knn(model, anchors, "item", k=k)     # hwer/validation.py:30-35: serial per-anchor loop
+    return len(anchors)
+
+
+def cpu_baseline(table_sample, queries, k, full_rows, seconds):
+    """Single core (the reference path is serial by construction): queries/s on the sample, scaled by
+    sample_rows / catalogue_rows (a KD-tree in d = 128 degenerates to a linear scan)."""
+    model, users, build_s = build_cpu_model(table_sample, queries)
+    _cpu_loop((model, users[:2], k))
+    n, t0 = 0, time.time()
+    while time.time() - t0 < seconds and n < len(users):
+        n += _cpu_loop((model, users[n:n + 4], k))
+    dt = time.time() - t0
+    qps_sample = n / dt
+    scale = len(table_sample) / float(full_rows)
+    return {"value": qps_sample * scale, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/hwer_oracle.py restatement of find_closest_neighbours (sklearn KDTree, float64) on the "
+                      "first %d rows of the catalogue, %d queries in %.1f s = %.2f q/s on the sample, scaled by "
+                      "%d/%d rows; KD-tree build %.1f s not included" % (len(table_sample), n, dt, qps_sample,
+                                                                        len(table_sample), full_rows, build_s)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    rows = min(a.cpu_sample_rows, a.items)
+    cores = os.cpu_count() or 1
+    table = cpu_table(rows, a.dim)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hwer_oracle as O
+    per_step = max(cores * 2, 16)
+    rs = np.random.RandomState(2)
+    queries = O.unit_length(rs.standard_normal((per_step, a.dim)).astype(np.float32), axis=1)
+    global _CPU_MODEL
+    model, users, build_s = build_cpu_model(table, queries)
+    _CPU_MODEL = model
+    ctx = mp.get_context("fork")                    # workers share the built trees copy-on-write
+    slices = [users[i::cores] for i in range(cores)]
+    slices = [s for s in slices if s]
+    with ctx.Pool(len(slices)) as pool:
+        def step():
+            return sum(pool.map(_cpu_loop, [(None, s, a.k) for s in slices]))
+        for _ in range(a.warmup):
+            step()
+        t0 = time.time()
+        n = 0
+        for _ in range(a.steps):
+            n += step()
+        dt = time.time() - t0
+    scale = rows / float(a.items)
+    v = n / dt * scale
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: 10M x 128 catalogue, exact top-%d, the reference's serial KD-tree loop run on "
+                                   "every host core in parallel" % a.k, "items": a.items, "dim": a.dim, "k": a.k,
+                       "queries_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": len(slices), "kind": "port",
+                             "sample": "oracle port of hwer find_closest_neighbours (sklearn KDTree float64) on a %d-row "
+                                       "sample, %d queries per step over %d forked workers, scaled by %d/%d rows; tree "
+                                       "build %.1f s excluded" % (rows, per_step, len(slices), rows, a.items, build_s)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def make_shard(hw, torch, a, begin, end, dev):
+    """Rows [begin, end) of the global table V = unit(alpha unit(C) + (1-alpha) unit(G)); chunk c of CHUNK rows is
+    generated from seeds (c, 10^6 + c), so the catalogue does not depend on the shard count."""
+    table = torch.empty((end - begin, a.dim), dtype=torch.float32, device=dev)
+    shadow = torch.empty((end - begin, hw.ops.shadow_width(a.dim)), dtype=torch.bfloat16, device=dev)
+    blend_ms, blend_bytes = 0.0, 0
+    for c in range(begin // CHUNK, (end + CHUNK - 1) // CHUNK):
+        cb, ce = c * CHUNK, min((c + 1) * CHUNK, a.items)
+        g1 = torch.Generator(device=dev).manual_seed(c)
+        g2 = torch.Generator(device=dev).manual_seed(1_000_000 + c)
+        content = torch.randn((ce - cb, a.dim), generator=g1, device=dev)
+        collab = torch.randn((ce - cb, a.dim), generator=g2, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t, s = hw.ops.blend_normalize(content, collab, a.alpha)
+        e1.record()
+        torch.cuda.synchronize()
+        blend_ms += e0.elapsed_time(e1)
+        blend_bytes += (ce - cb) * a.dim * (4 + 4 + 4) + (ce - cb) * s.shape[1] * 2
+        lo, hi = max(cb, begin), min(ce, end)
+        table[lo - begin:hi - begin] = t[lo - cb:hi - cb]
+        shadow[lo - begin:hi - begin] = s[lo - cb:hi - cb]
+        del content, collab, t, s
+    return table, shadow, blend_ms, blend_bytes
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import hwer_b200 as hw
+    from hwer_b200 import _native
+    _native.lib()                                    # fail loudly now if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    begin, end = hw.sharded.partition(a.items, world, rank)
+    table, shadow, blend_ms, blend_bytes = make_shard(hw, torch, a, begin, end, dev)
+    viol, _, _, _, max_norm = hw.ops.norm_stats(table)
+    assert viol == 0
+    shard = hw.sharded.ShardedTopK(table, begin, shadow=shadow, max_norm=max_norm)
+    index = shard.index
+    d_pad = shadow.shape[1]
+
+    def queries_for(B):
+        g = torch.Generator(device=dev).manual_seed(2)
+        return hw.ops.unit_length(torch.randn((B, a.dim), generator=g, device=dev))
+
+    def step_device(q):
+        idx, _, s64 = index.topk_async(q, min(a.k, index.n), a.mode, idx_offset=begin, want_f64=True)
+        if world > 1:
+            idx, s64 = hw.sharded.pad_local_result(idx, s64, a.k)
+            gs, gi = hw.sharded.gather_shard_results(idx, s64)
+            return hw.ops.merge_topk(gs, gi)
+        return idx, s64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(B, steps, warmup, profile):
+        q = queries_for(B)
+        for _ in range(warmup):
+            step_device(q)
+        rc, need = index.finish()
+        if rc != 0:
+            raise RuntimeError("candidate overflow in warm-up (needed cap %d)" % need)
+        index.profile(profile)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = step_device(q)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        rc, need = index.finish()
+        if rc != 0:
+            raise RuntimeError("candidate overflow in the timed region (needed cap %d)" % need)
+        filt_ms, filt_l, other_l = index.profile_read() if profile else (0.0, 0, 0)
+        index.profile(False)
+        return ms, filt_ms, filt_l, other_l, out
+
+    def roofline(B, filt_ms_per_step):
+        rows = end - begin
+        if B >= 256:
+            flops = 2.0 * B * rows * a.dim
+            ach = flops / (filt_ms_per_step * 1e-3) / 1e12
+            return {"bound": "tensor", "achieved": ach, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tc_sustained"], "traffic": None, "basis": pk["basis"] + " (sustained bf16)",
+                    "kernel": "score_filter_tc_kernel", "ms_per_step": filt_ms_per_step}
+        byt = rows * d_pad * 2.0 + B * a.dim * 4.0 + B * a.k * 8.0
+        ach = byt / (filt_ms_per_step * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": None, "basis": pk["basis"] + " (copy bandwidth)", "kernel": "score_filter_tc_kernel",
+                "ms_per_step": filt_ms_per_step}
+
+    # ---- headline: device-resident throughput (events on the launching stream), clocks sampled meanwhile
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, _, _, _, out = measure(a.batch, a.steps, a.warmup, profile=False)
+    clocks = sampler.stop() if sampler else None
+    # same steps again with the filter kernel bracketed by events: kernel time for the roofline + launch counts
+    pms, filt_ms, filt_l, other_l, _ = measure(a.batch, a.steps, 1, profile=True)
+    launches_per_step = (filt_l + other_l) / a.steps + (1 if world > 1 else 0)
+    roof = roofline(a.batch, filt_ms / a.steps)
+    roof["share_of_step"] = (filt_ms / a.steps) / (pms / a.steps)
+
+    # ---- end to end through the public API: pinned host queries in, results out, every step
+    q_host = queries_for(a.batch).cpu().pin_memory()
+    idx_host = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
+    sc_host = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        q = q_host.to(dev, non_blocking=True)
+        if world > 1:
+            idx, sc = shard.topk(q, a.k, a.mode)
+        else:
+            idx, sc = index.topk(q, a.k, a.mode, idx_offset=begin)
+        idx_host.copy_(idx, non_blocking=True)
+        sc_host.copy_(sc, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, a.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, a.steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    sweep = {}
+    if world == 1 and a.sweep:
+        for B in [int(x) for x in a.sweep.split(",") if x]:
+            st = max(a.steps, 20)
+            sms, sf, _, _, _ = measure(B, st, a.warmup, profile=False)
+            _, sf, _, _, _ = measure(B, st, 1, profile=True)
+            r = roofline(B, sf / st)
+            sweep[str(B)] = {"value": B * st / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / st, "roofline": r}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            rows = min(a.cpu_sample_rows, end - begin)
+            cpu = cpu_baseline(table[:rows].cpu().numpy(), queries_for(64).cpu().numpy(), a.k, a.items, a.cpu_seconds)
+        idx_chk = out[0]
+        line = {
+            "metric": METRIC, "value": a.batch * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 tensor-core filter + f64 re-score" if a.mode == "exact" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "C4: synthetic 10M x 128 unit-norm catalogue (alpha=%.2f blend of two seeded Gaussian "
+                                   "tables), exact top-%d by cosine, query batch %d, item-sharded over %d GPU(s)"
+                                   % (a.alpha, a.k, a.batch, world),
+                       "items": a.items, "dim": a.dim, "k": a.k, "batch": a.batch, "mode": a.mode,
+                       "parallelism": "item-shard x%d + all-gather/merge" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (%.2f GB bf16 shadow per GPU streamed every step)"
+                             % ((end - begin) * d_pad * 2 / 1e9)},
+            "e2e": {"value": a.batch * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(round(launches_per_step * a.steps)),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sweep": sweep,
+            "blend_normalize": {"achieved": blend_bytes / (blend_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": blend_bytes / (blend_ms * 1e-3) / 1e9 / pk["hbm"], "bound": "hbm"},
+            "result_checksum": int(idx_chk.sum().item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

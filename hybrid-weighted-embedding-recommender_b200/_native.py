@@ -32,6 +32,8 @@ SIGNATURES = {
     "hwer_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_uint32, c_int64, c_void_p, c_void_p,
                           c_void_p, c_void_p]),
     "hwer_topk_finish": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
+    "hwer_profile": (c_int, [c_void_p, c_int]),
+    "hwer_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
     "hwer_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "hwer_merge_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hwer_pair_score": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/hwer_b200.h"
 #include "kernels.h"
@@ -73,6 +75,11 @@ struct hwer_index {
     unsigned int* needed_dev = nullptr;
     unsigned int* needed_host = nullptr;   // pinned
     unsigned int last_cap = 0;
+    // optional live profiling of the dominant (filter) kernel with CUDA events on the launching stream
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t ev_used = 0;
+    long long filter_launches = 0, other_launches = 0;
 };
 
 namespace {
@@ -98,6 +105,20 @@ int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
     ix->ws_queries = q;
     ix->ws_cap = c;
     return HWER_OK;
+}
+
+bool prof_begin(hwer_index* ix, cudaStream_t stream) {
+    if (!ix->prof) return false;
+    if (ix->ev_used == ix->ev.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+        ix->ev.emplace_back(a, b);
+    }
+    cudaEventRecord(ix->ev[ix->ev_used].first, stream);
+    return true;
+}
+void prof_end(hwer_index* ix, cudaStream_t stream, bool began) {
+    if (began) cudaEventRecord(ix->ev[ix->ev_used++].second, stream);
 }
 
 struct Schedule {
@@ -227,6 +248,7 @@ int hwer_index_destroy(hwer_index_t* ix) {
     if (ix->margin) cudaFree(ix->margin);
     if (ix->needed_dev) cudaFree(ix->needed_dev);
     if (ix->needed_host) cudaFreeHost(ix->needed_host);
+    for (auto& e : ix->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete ix;
     return HWER_OK;
 }
@@ -271,12 +293,14 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
             HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->margin, stream));
             margin = ix->margin;
         }
+        ix->other_launches += margin ? 3 : 2;   // fill + (margin) + final
         long long seen = 0;
         int round = 0;
         while (seen < T) {
             long long take = round == 0 ? sch.first_tiles : seen * sch.growth;
             long long end = seen + take;
             if (end > T || (T - end) * 4 < take) end = T;
+            const bool timed = prof_begin(ix, stream);
             if (ix->use_tc) {
                 hwer::FilterParams p;
                 memset(&p, 0, sizeof p);
@@ -295,8 +319,11 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 HWER_CUDA(hwer::launch_filter_simt(ix->table, ix->n, ix->d, Q, Bc, ix->thr, ix->cand, ix->cnt, sch.cap,
                                                    rb, re, ix->num_sms, stream));
             }
+            prof_end(ix, stream, timed);
             HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, margin, ix->thr, ix->needed_dev,
                                                   stream));
+            ix->filter_launches += 1;
+            ix->other_launches += 1;
             seen = end;
             ++round;
         }
@@ -323,6 +350,33 @@ int hwer_topk_finish(hwer_index_t* ix, void* stream_v, uint32_t* needed_cap) {
                  ix->last_cap, need);
         return fail(HWER_E_OVERFLOW, buf);
     }
+    return HWER_OK;
+}
+
+int hwer_profile(hwer_index_t* ix, int enable) {
+    if (!ix) return fail(HWER_E_INVALID, "hwer_profile: null index");
+    ix->prof = enable != 0;
+    ix->ev_used = 0;
+    ix->filter_launches = ix->other_launches = 0;
+    return HWER_OK;
+}
+
+int hwer_profile_read(hwer_index_t* ix, void* stream_v, double* filter_ms, int64_t* filter_launches,
+                      int64_t* other_launches) {
+    if (!ix) return fail(HWER_E_INVALID, "hwer_profile_read: null index");
+    HWER_CUDA(cudaSetDevice(ix->device));
+    HWER_CUDA(cudaStreamSynchronize((cudaStream_t)stream_v));
+    double ms = 0.0;
+    for (size_t i = 0; i < ix->ev_used; ++i) {
+        float t = 0.f;
+        HWER_CUDA(cudaEventElapsedTime(&t, ix->ev[i].first, ix->ev[i].second));
+        ms += t;
+    }
+    if (filter_ms) *filter_ms = ms;
+    if (filter_launches) *filter_launches = ix->filter_launches;
+    if (other_launches) *other_launches = ix->other_launches;
+    ix->ev_used = 0;
+    ix->filter_launches = ix->other_launches = 0;
     return HWER_OK;
 }
 

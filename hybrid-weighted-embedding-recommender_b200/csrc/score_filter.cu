@@ -160,7 +160,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             }
             for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
                 const int q = q_base + i;
-                thr_s[i] = (q < p.B) ? p.thr[q] : __int_as_float(0x7f800000);
+                thr_s[i] = (q < p.B) ? (DUMP ? 0.0f : p.thr[q]) : __int_as_float(0x7f800000);
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
         }

@@ -167,6 +167,17 @@ class TopKIndex:
             cap = need
         N.check(rc)
 
+    def profile(self, enable=True):
+        N.check(N.lib().hwer_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(filter-kernel ms, filter launches, other kernel launches) since the last read; synchronises."""
+        ms, fl, ol = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_profile_read(self._h, _stream(self.device), ctypes.byref(ms), ctypes.byref(fl),
+                                              ctypes.byref(ol)))
+        return ms.value, fl.value, ol.value
+
     def debug_scores(self, queries):
         queries = _need(queries, torch.float32, "queries", 2)
         out = torch.zeros((self.n, queries.shape[0]), dtype=torch.float32, device=self.device)

@@ -89,6 +89,13 @@ int hwer_topk(hwer_index_t* index, const float* queries_dev, int32_t B, int32_t 
 /* Synchronises `stream` and reports candidate-list overflow of the topk calls enqueued since the last finish. */
 int hwer_topk_finish(hwer_index_t* index, void* stream, uint32_t* needed_cap);
 
+/* Measurement aid: when enabled, every score-filter launch of hwer_topk is bracketed by CUDA events on the
+ * launching stream.  hwer_profile_read synchronises `stream`, returns the summed filter-kernel time and the
+ * number of kernels launched (filter / everything else) since the last read, and resets the counters. */
+int hwer_profile(hwer_index_t* index, int enable);
+int hwer_profile_read(hwer_index_t* index, void* stream, double* filter_ms, int64_t* filter_launches,
+                      int64_t* other_launches);
+
 /* Debug/validation aid: the full bf16 tensor-core score matrix out[n, ld] (ld >= B) for small problems. */
 int hwer_debug_scores(hwer_index_t* index, const float* queries_dev, int32_t B, float* out_dev, int64_t ld,
                       void* stream);

@@ -1,0 +1,126 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hwer_b200.h declares; the host-side mirror keeps
+the reference's semantics; nothing silently falls back to the CPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hwer_b200
+from hwer_b200 import _native
+from hwer_b200.recommendation_base import Edge, Node, NodeIndex, RecommendationBase
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "hwer_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hwer_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.lib()
+    declared = _header_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), "libhwer_b200.so does not export %s" % name
+    assert sorted(_native.SIGNATURES) == declared, "ctypes table and header disagree"
+    assert lib.hwer_version() == 100
+    assert lib.hwer_shadow_width(1) == 64 and lib.hwer_shadow_width(128) == 128 and lib.hwer_shadow_width(129) == 192
+
+
+def test_library_is_sm100a_tcgen05_code():
+    """The shipped kernels are Blackwell-native: tcgen05 MMA, TMEM loads and TMA appear in the SASS."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _native.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_argument_validation_without_gpu():
+    lib = _native.lib()
+    assert lib.hwer_topk(None, None, 1, 1, 0, 0, 0, None, None, None, None) == _native.HWER_E_INVALID
+    assert b"hwer_topk" in lib.hwer_last_error()
+    assert lib.hwer_pair_score(None, 1, 1, None, None, 1, None, None) == _native.HWER_E_INVALID
+    assert lib.hwer_index_destroy(None) == 0
+
+
+def test_no_cpu_fallback():
+    t = torch.zeros(4, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hwer_b200.ops.norm_stats(t)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hwer_b200.ops.blend_normalize(None, t)
+    if not torch.cuda.is_available():
+        class R(RecommendationBase):
+            def fit(self, *a, **k):
+                pass
+        r = R({"user"}, 8)
+        r.add_nodes([Node("user", i) for i in range(4)])
+        with pytest.raises(RuntimeError, match="CUDA"):
+            r.__build_knn__(np.eye(4, 8, dtype=np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hybrid-weighted-embedding-recommender_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "hwer_oracle" not in text and "ref_shim" not in text, f
+                assert "/root/reference" not in text, f
+
+
+def test_node_edge_semantics():
+    # hwer/recommendation_base.py:19-61
+    assert Node("user", 1) == Node("user", "1") and hash(Node("user", 1)) == hash(Node("user", "1"))
+    assert Node("user", 1) != Node("item", 1)
+    assert repr(Node("item", 7)) == "('item', '7')"
+    e = Edge(Node("user", 1), Node("item", 2), 4.0)
+    u, i, w = e
+    assert (u, i, w) == (Node("user", 1), Node("item", 2), 4.0)
+    assert e == Edge(Node("user", "1"), Node("item", "2"), 4.0) and len({e, Edge(u, i, 4.0)}) == 1
+
+
+def test_add_nodes_contract():
+    class R(RecommendationBase):
+        def fit(self, *a, **k):
+            pass
+    r = R({"user", "item"}, 8)
+    users = [Node("user", i) for i in range(3)]
+    r.add_nodes(users)
+    r.add_nodes([Node("item", 0)])
+    assert r.nodes_to_idx[Node("item", 0)] == 3 and r.nodes_to_idx.inverse[1] == Node("user", 1)
+    with pytest.raises(AssertionError):
+        r.add_nodes([Node("user", 0)])                # already present   (:98)
+    with pytest.raises(AssertionError):
+        r.add_nodes([Node("item", 5), Node("item", 5)])   # duplicates    (:97)
+    with pytest.raises(AssertionError):
+        r.add_nodes([Node("genre", 1)])               # unknown type      (:99)
+    with pytest.raises(AssertionError):
+        r.find_closest_neighbours("item", users[0])   # not fitted        (:159)
+
+
+def test_node_index_inverse_tracks_updates():
+    ix = NodeIndex()
+    ix.update({Node("a", 1): 0})
+    assert ix.inverse[0] == Node("a", 1)
+    ix[Node("a", 2)] = 1
+    assert ix.inverse[1] == Node("a", 2)
+
+
+def test_partition_covers_rows_exactly():
+    from hwer_b200.sharded import partition
+    for n in (1, 7, 128, 10_000_000, 500_000_000):
+        for w in (1, 2, 4, 8):
+            spans = [partition(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
