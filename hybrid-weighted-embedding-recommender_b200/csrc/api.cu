@@ -312,6 +312,7 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 p.thr = ix->thr; p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
                 p.n_items = ix->n; p.tile_begin = (int)seen; p.tile_end = (int)end;
                 p.tile_mul = ix->tile_mul; p.tile_mod = T;
+                p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics
                 HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
             } else {
                 long long rb = seen * hwer::kTileItems, re = end * hwer::kTileItems;
@@ -320,8 +321,9 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                                                    rb, re, ix->num_sms, stream));
             }
             prof_end(ix, stream, timed);
-            HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, margin, ix->thr, ix->needed_dev,
-                                                  stream));
+            const int fixed = (ix->use_tc && round == 0) ? (int)((end - seen) * hwer::kTileItems) : -1;
+            HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
+                                                  ix->needed_dev, stream));
             ix->filter_launches += 1;
             ix->other_launches += 1;
             seen = end;

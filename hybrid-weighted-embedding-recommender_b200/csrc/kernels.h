@@ -41,6 +41,7 @@ struct FilterParams {
     int acc_stages;           // TMEM accumulator stages
     int tmem_cols;            // power of two >= acc_stages * nq
     int stream_once;          // 1: item tiles are read by one CTA only -> L2 evict-first
+    int dense;                // 1: round 0, every score is written at its position in the round (no atomics)
     float* dump;              // debug: full score matrix [n_items, dump_ld] (nullptr in production)
     long long dump_ld;
 };
@@ -59,7 +60,8 @@ cudaError_t launch_query_margin(const float* queries, int B, int d, float factor
 cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream);
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
-                                  const float* margin, float* thr, unsigned int* needed_cap, cudaStream_t stream);
+                                  int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
+                                  cudaStream_t stream);
 
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,

@@ -23,7 +23,11 @@ namespace hwer {
 namespace {
 
 constexpr int kSlabBytes = kTileItems * 128;  // one 64-wide K block of an item tile: 16 KB
-constexpr int kThreadsTc = 192;
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant, splitting the query columns
+constexpr int kThreadsTc = (2 + kEpiWarps) * 32;
+constexpr int kHitQueue = 64;                 // per-warp shared-memory hit queue (entries)
+
+enum : int { kModeFilter = 0, kModeDump = 1, kModeDense = 2 };
 
 __device__ __forceinline__ void append_candidate(unsigned long long* cand, unsigned int* cnt, unsigned int cap,
                                                  int q, float s, uint32_t row) {
@@ -31,19 +35,93 @@ __device__ __forceinline__ void append_candidate(unsigned long long* cand, unsig
     if (slot < cap) cand[(size_t)q * cap + slot] = make_key(s, row);
 }
 
-// Compare W accumulator columns of one catalogue row against the thresholds of
-// the W queries they belong to; the hit path is rare and kept
-// out of line in 8-column groups.
-template <int W, bool DUMP>
+// Per-warp hit queue.  Hits are rare (DESIGN.md "hit rate"), so the epilogue only parks them in shared memory
+// with warp-uniform ballots; the global atomicAdd that allocates a slot in the query's candidate list is issued
+// at the start of the NEXT tile and its result is consumed at that tile's end, so the ~1 us L2 round trip
+// overlaps a whole tile of compare work instead of stalling the warp.
+// Out of line on purpose: it is expanded at 32+ call sites otherwise and the epilogue outgrows the I-cache.
+__device__ __noinline__ void hit_queue_flush(const uint4* slots, int count, unsigned long long* cand,
+                                             unsigned int* cnt, unsigned int cap) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int base = 0; base < count; base += 32) {
+        if (base + lane < count) {
+            const uint4 e = slots[base + lane];
+            const unsigned int slot = atomicAdd(&cnt[e.z], 1u);
+            if (slot < cap) cand[(size_t)e.z * cap + slot] = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+        }
+    }
+    __syncwarp();
+}
+
+struct HitQueue {
+    uint4* slots;     // [kHitQueue] {key lo, key hi, query, -}
+    int count;        // warp-uniform
+
+    __device__ __forceinline__ void flush_blocking(const FilterParams& p, int lane) {
+        (void)lane;
+        hit_queue_flush(slots, count, p.cand, p.cnt, p.cap);
+        count = 0;
+    }
+    // one query column: `hit` lanes park their (score, row); at most 32 entries
+    __device__ __forceinline__ void push(bool hit, float s, uint32_t row, int q, const FilterParams& p, int lane) {
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            if (count + 32 > kHitQueue) flush_blocking(p, lane);
+            if (hit) {
+                const unsigned long long k = make_key(s, row);
+                slots[count + __popc(m & ((1u << lane) - 1u))] = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)q, 0u);
+            }
+            count += __popc(m);
+        }
+    }
+};
+
+// 1 if any of eight scores reaches its threshold (NaN never does).
+__device__ __forceinline__ uint32_t any_ge8(const uint32_t* v, const float* t) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.ge.f32 p, %1, %9;\n\t"
+        "setp.ge.f32 q, %2, %10;\n\t"
+        "setp.ge.or.f32 p, %3, %11, p;\n\t"
+        "setp.ge.or.f32 q, %4, %12, q;\n\t"
+        "setp.ge.or.f32 p, %5, %13, p;\n\t"
+        "setp.ge.or.f32 q, %6, %14, q;\n\t"
+        "setp.ge.or.f32 p, %7, %15, p;\n\t"
+        "setp.ge.or.f32 q, %8, %16, q;\n\t"
+        "or.pred p, p, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "f"(__uint_as_float(v[0])), "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[2])),
+          "f"(__uint_as_float(v[3])), "f"(__uint_as_float(v[4])), "f"(__uint_as_float(v[5])),
+          "f"(__uint_as_float(v[6])), "f"(__uint_as_float(v[7])), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]),
+          "f"(t[4]), "f"(t[5]), "f"(t[6]), "f"(t[7]));
+    return r;
+}
+
+// Compare W accumulator columns of one catalogue row against the thresholds of the W queries they belong to.
+template <int W, int MODE>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const float* thr_s, int c0, int q_base,
-                                               long long row, bool row_ok, const FilterParams& p) {
-    if (DUMP) {
+                                               long long row, bool row_ok, const FilterParams& p, HitQueue& hq,
+                                               int lane, long long dense_pos) {
+    if (MODE == kModeDump) {
         if (row_ok) {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 int q = q_base + c0 + j;
                 if (q < p.B) p.dump[(size_t)row * p.dump_ld + q] = __uint_as_float(v[j]);
             }
+        }
+        return;
+    }
+    if (MODE == kModeDense) {
+        // round 0 (open threshold): every score is a candidate, slot = position in the round, no atomics;
+        // for a fixed query the 32 lanes write 32 consecutive keys (256 B, coalesced)
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int q = q_base + c0 + j;
+            const float s = __uint_as_float(v[j]);
+            if (q < p.B) p.cand[(size_t)q * p.cap + dense_pos] = (row_ok && s == s) ? make_key(s, (uint32_t)row) : 0ull;
         }
         return;
     }
@@ -54,28 +132,29 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const flo
         float4 x = t4[j];
         t[4 * j + 0] = x.x; t[4 * j + 1] = x.y; t[4 * j + 2] = x.z; t[4 * j + 3] = x.w;
     }
-    bool any = false;
+    // Eight columns per asm block, two predicate chains per block, blocks independent: the serial
+    // FSETP...OR chain NVVM would otherwise build is issue-latency bound (ncu: "wait" stalls dominate).
+    uint32_t grp[W / 8];
 #pragma unroll
-    for (int j = 0; j < W; ++j) any |= (__uint_as_float(v[j]) >= t[j]);
-    if (any && row_ok) {
+    for (int g = 0; g < W / 8; ++g) grp[g] = any_ge8(&v[8 * g], &t[8 * g]);
+    uint32_t anyw = 0;
+#pragma unroll
+    for (int g = 0; g < W / 8; ++g) anyw |= grp[g];
+    if (__any_sync(0xffffffffu, anyw && row_ok)) {          // warp-uniform from here on: no divergence
 #pragma unroll
         for (int g = 0; g < W / 8; ++g) {
-            bool anyg = false;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) anyg |= (__uint_as_float(v[8 * g + j]) >= t[8 * g + j]);
-            if (anyg) {
+            if (__any_sync(0xffffffffu, grp[g] && row_ok)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float s = __uint_as_float(v[8 * g + j]);
-                    if (s >= t[8 * g + j])
-                        append_candidate(p.cand, p.cnt, p.cap, q_base + c0 + 8 * g + j, s, (uint32_t)row);
+                    const float s = __uint_as_float(v[8 * g + j]);
+                    hq.push((s >= t[8 * g + j]) & row_ok, s, (uint32_t)row, q_base + c0 + 8 * g + j, p, lane);
                 }
             }
         }
     }
 }
 
-template <bool DUMP>
+template <int MODE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -90,7 +169,8 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     uint8_t* q_smem = smem;
     uint8_t* item_smem = q_smem + kb * q_slab;   // kb*q_slab is a multiple of 1024 (nq % 8 == 0)
     float* thr_s = reinterpret_cast<float*>(item_smem + (size_t)p.stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + kMaxNQ);
+    uint4* hitq_s = reinterpret_cast<uint4*>(thr_s + kMaxNQ);                   // [kEpiWarps][kHitQueue]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hitq_s + kEpiWarps * kHitQueue);
     uint64_t* full_bar = bars;                            // [stages]   TMA -> MMA
     uint64_t* empty_bar = bars + p.stages;                // [stages]   MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * p.stages;            // [acc]      MMA -> epilogue
@@ -108,7 +188,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         }
         for (int i = 0; i < p.acc_stages; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);   // one arrival per epilogue warp
+            mbar_init(&tempty_bar[i], kEpiWarps);   // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -160,7 +240,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             }
             for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
                 const int q = q_base + i;
-                thr_s[i] = (q < p.B) ? (DUMP ? 0.0f : p.thr[q]) : __int_as_float(0x7f800000);
+                thr_s[i] = (q < p.B) ? (MODE == kModeFilter ? p.thr[q] : 0.0f) : __int_as_float(0x7f800000);
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
         }
@@ -207,32 +287,61 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             }
             __syncwarp();
         } else {
-            // ===================== epilogue (4 warps) =====================
+            // ===================== epilogue (8 warps) =====================
+            const int e = warp - 2;
             const uint32_t quad = (uint32_t)warp & 3u;   // TMEM lane quadrant this warp may read
+            const int half = e >> 2;                      // which half of the 32-column chunks this warp takes
+            HitQueue hq;
+            hq.slots = hitq_s + e * kHitQueue;
+            hq.count = 0;
             for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+                // deferred appends of the previous tile's hits: issue the slot-allocating atomics now ...
+                int pend = 0;
+                unsigned long long pkey = 0ull;
+                unsigned int pq = 0u, pslot = 0u;
+                if (MODE == kModeFilter && hq.count > 0) {
+                    if (hq.count > 32) {
+                        hq.flush_blocking(p, lane);
+                    } else {
+                        pend = hq.count;
+                        if (lane < pend) {
+                            const uint4 en = hq.slots[lane];
+                            pkey = (unsigned long long)en.x | ((unsigned long long)en.y << 32);
+                            pq = en.z;
+                            pslot = atomicAdd(&p.cnt[pq], 1u);
+                        }
+                        hq.count = 0;
+                        __syncwarp();
+                    }
+                }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after_sync();
+                const long long tile_pos = t - p.tile_begin;
                 const long long row = (((long long)t * p.tile_mul) % p.tile_mod) * kTileItems + quad * 32 + lane;
                 const bool row_ok = row < p.n_items;
+                const long long dense_pos = tile_pos * kTileItems + quad * 32 + lane;
                 const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * (uint32_t)nq;
-                int c0 = 0;
-                for (; c0 + 32 <= nq; c0 += 32) {
+                int c0 = 32 * half;
+                for (; c0 + 32 <= nq; c0 += 64) {
                     uint32_t v[32];
                     tmem_ld_x32(taddr + c0, v);
                     tmem_ld_wait();
-                    epilogue_chunk<32, DUMP>(v, thr_s, c0, q_base, row, row_ok, p);
+                    epilogue_chunk<32, MODE>(v, thr_s, c0, q_base, row, row_ok, p, hq, lane, dense_pos);
                 }
-                if (c0 < nq) {
+                if (c0 < nq && c0 + 16 == nq) {          // a trailing 16-column chunk belongs to exactly one half
                     uint32_t v[16];
                     tmem_ld_x16(taddr + c0, v);
                     tmem_ld_wait();
-                    epilogue_chunk<16, DUMP>(v, thr_s, c0, q_base, row, row_ok, p);
+                    epilogue_chunk<16, MODE>(v, thr_s, c0, q_base, row, row_ok, p, hq, lane, dense_pos);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                // ... and consume their results only now, a whole tile of work later
+                if (lane < pend && pslot < p.cap) p.cand[(size_t)pq * p.cap + pslot] = pkey;
             }
+            if (MODE == kModeFilter) hq.flush_blocking(p, lane);
         }
         // All MMAs reading this query block have retired once every epilogue warp is here.
         __syncthreads();
@@ -310,7 +419,7 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
 
 size_t filter_tc_smem_bytes(int nq, int kb, int stages) {
     return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + kMaxNQ * sizeof(float) +
-           (2 * stages + 8) * sizeof(uint64_t) + 16;
+           (size_t)kEpiWarps * kHitQueue * sizeof(uint4) + (2 * stages + 8) * sizeof(uint64_t) + 16;
 }
 
 int filter_tc_pick_stages(int nq, int kb) {
@@ -342,16 +451,20 @@ cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sm
     }
     p.stream_once = (p.nqb == 1) ? 1 : 0;
     const size_t smem = filter_tc_smem_bytes(p.nq, p.kb, p.stages);
-    cudaError_t e;
-    if (p.dump) {
-        e = cudaFuncSetAttribute(score_filter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        score_filter_tc_kernel<true><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
-    } else {
-        e = cudaFuncSetAttribute(score_filter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        score_filter_tc_kernel<false><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
+    static bool attr_done = false;   // the opt-in shared-memory ceiling is a per-function, per-process setting
+    if (!attr_done) {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(score_filter_tc_kernel<kModeFilter>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(score_filter_tc_kernel<kModeDump>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(score_filter_tc_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
+        attr_done = true;
     }
+    if (p.dump)
+        score_filter_tc_kernel<kModeDump><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
+    else if (p.dense)
+        score_filter_tc_kernel<kModeDense><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
+    else
+        score_filter_tc_kernel<kModeFilter><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
     return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@ namespace hwer {
 namespace {
 
 constexpr int kSelThreads = 256;
+constexpr int kFinalThreads = 512;   // 16 warps re-score candidates concurrently (row gathers are latency bound)
 
 __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
@@ -45,42 +46,90 @@ __device__ __forceinline__ void block_bitonic(int P, Before before, Swap swap) {
     }
 }
 
+// K-th largest key prefix by radix select (4 passes x 8 bits over the order-preserving score image), then an
+// unordered compaction of everything at or above the new threshold.  O(c) work per query; a full sort of the
+// list is only needed once, in final_kernel, over the ~1.4 K survivors.
 __global__ void __launch_bounds__(kSelThreads)
 select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap, int K,
-                      const float* __restrict__ margin, float* __restrict__ thr, unsigned int* needed_cap) {
+                      int fixed_count, const float* __restrict__ margin, float* __restrict__ thr,
+                      unsigned int* needed_cap) {
     extern __shared__ unsigned long long keys[];
-    __shared__ int kept_s;
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int sel_prefix, sel_remaining, kept_s, valid_s;
     const int q = blockIdx.x;
-    unsigned int c_raw = cnt[q];
+    unsigned int c_raw = fixed_count >= 0 ? (unsigned int)fixed_count : cnt[q];
     if (c_raw > cap) {
         if (threadIdx.x == 0) atomicMax(needed_cap, c_raw);
         c_raw = cap;
     }
     const int c = (int)c_raw;
-    const int P = next_pow2(c > 1 ? c : 2);
     unsigned long long* list = cand + (size_t)q * cap;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = (i < c) ? list[i] : 0ull;
-    if (threadIdx.x == 0) kept_s = 0;
+    if (threadIdx.x == 0) { sel_prefix = 0u; sel_remaining = (unsigned int)K; kept_s = 0u; valid_s = 0u; }
     __syncthreads();
-    block_bitonic(P, [&](int a, int b) { return keys[a] > keys[b]; },
-                  [&](int a, int b) { unsigned long long t = keys[a]; keys[a] = keys[b]; keys[b] = t; });
+    unsigned int nvalid = 0;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const unsigned long long k = list[i];
+        keys[i] = k;
+        nvalid += (k != 0ull) ? 1u : 0u;     // key 0 = empty slot of a dense round (tail rows, NaN scores)
+    }
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    if (lane_id() == 0 && nvalid) atomicAdd(&valid_s, nvalid);
+    __syncthreads();
     float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
-    if (c >= K) {
-        const float sk = key_score(keys[K - 1]);
+    if ((int)valid_s >= K) {
+        unsigned int mask = 0u;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            const unsigned int prefix = sel_prefix;
+            for (int i = threadIdx.x; i < c; i += blockDim.x) {
+                const unsigned long long k = keys[i];
+                const unsigned int hi = (unsigned int)(k >> 32);
+                if (k != 0ull && (hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                // lane l owns bins [8l, 8l+8); walk from the top bin down to the one holding the K-th key
+                const int l = threadIdx.x;
+                unsigned int mine = 0u;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) mine += hist[8 * l + b];
+                unsigned int above = mine;      // inclusive suffix sum over lanes >= l
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int x = __shfl_down_sync(0xffffffffu, above, o);
+                    if (l + o < 32) above += x;
+                }
+                const unsigned int rem = sel_remaining;
+                const unsigned int strictly_above = above - mine;      // keys in bins of higher lanes
+                if (strictly_above < rem && rem <= above) {
+                    unsigned int acc = strictly_above;
+                    for (int b = 7; b >= 0; --b) {
+                        const unsigned int h = hist[8 * l + b];
+                        if (acc + h >= rem) {
+                            sel_prefix = prefix | ((unsigned int)(8 * l + b) << shift);
+                            sel_remaining = rem - acc;
+                            break;
+                        }
+                        acc += h;
+                    }
+                }
+            }
+            mask |= 255u << shift;
+            __syncthreads();
+        }
+        const float sk = ordered_to_f32(sel_prefix);
         const float m = margin ? margin[q] : 0.0f;
         t = sk - m;
         if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
     }
-    // keys are sorted descending: count the prefix still at or above the new threshold
-    int local = 0;
-    for (int i = threadIdx.x; i < c; i += blockDim.x) local += (key_score(keys[i]) >= t) ? 1 : 0;
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if (lane_id() == 0 && local) atomicAdd(&kept_s, local);
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (k != 0ull && key_score(k) >= t) list[atomicAdd(&kept_s, 1u)] = k;
+    }
     __syncthreads();
-    const int kept = kept_s;
-    for (int i = threadIdx.x; i < kept; i += blockDim.x) list[i] = keys[i];
     if (threadIdx.x == 0) {
-        cnt[q] = (unsigned int)kept;
+        cnt[q] = kept_s;
         thr[q] = t;
     }
 }
@@ -94,7 +143,7 @@ __device__ __forceinline__ double exact_dot(const float* __restrict__ x, const f
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kFinalThreads)
 final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned int cap,
              int K, const float* __restrict__ table, int d, const float* __restrict__ queries, long long idx_offset,
              long long* __restrict__ out_idx, float* __restrict__ out_score, double* __restrict__ out_score64,
@@ -115,11 +164,12 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
         const float* qv = queries + (size_t)q * d;
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for (int i = warp; i < c; i += nwarps) {
-            const uint32_t row = key_row(list[i]);
-            const double s = exact_dot(table + (size_t)row * d, qv, d);
+            const unsigned long long k = list[i];
+            const uint32_t row = key_row(k);
+            const double s = (k != 0ull) ? exact_dot(table + (size_t)row * d, qv, d) : 0.0;
             if (lane_id() == 0) {
-                sk[i] = f64_to_ordered(s);
-                rw[i] = row;
+                sk[i] = (k != 0ull && s == s) ? f64_to_ordered(s) : 0ull;
+                rw[i] = (k != 0ull && s == s) ? row : 0xffffffffu;
             }
         }
         for (int i = c + threadIdx.x; i < P; i += blockDim.x) { sk[i] = 0ull; rw[i] = 0xffffffffu; }
@@ -127,7 +177,7 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
         for (int i = threadIdx.x; i < P; i += blockDim.x) {
             const unsigned long long k = (i < c) ? list[i] : 0ull;
             sk[i] = k >> 32;
-            rw[i] = (i < c) ? key_row(k) : 0xffffffffu;
+            rw[i] = (k != 0ull) ? key_row(k) : 0xffffffffu;
         }
     }
     __syncthreads();
@@ -139,7 +189,7 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
                   });
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         const size_t o = (size_t)q * K + i;
-        if (i < c) {
+        if (i < c && rw[i] != 0xffffffffu) {
             const double s = EXACT ? ordered_to_f64(sk[i]) : (double)ordered_to_f32((uint32_t)sk[i]);
             out_idx[o] = (long long)rw[i] + idx_offset;
             out_score[o] = (float)s;
@@ -190,6 +240,7 @@ merge_kernel(const double* __restrict__ scores, const long long* __restrict__ id
     }
 }
 
+// Raises a kernel's opt-in dynamic shared-memory ceiling (static shared memory counts against the same 227 KB).
 template <class Kern>
 cudaError_t set_smem(Kern k, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -205,12 +256,15 @@ inline size_t pow2_ge(size_t v) {
 }  // namespace
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
-                                  const float* margin, float* thr, unsigned int* needed_cap, cudaStream_t stream) {
+                                  int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
+                                  cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    const size_t smem = pow2_ge(cap) * sizeof(unsigned long long);
+    // stage only what can be there: a dense round holds fixed_count keys, a filter round at most cap
+    const size_t n = fixed_count >= 0 ? (size_t)fixed_count : (size_t)cap;
+    const size_t smem = (n < 1024 ? 1024 : n) * sizeof(unsigned long long);
     cudaError_t e = set_smem(select_compact_kernel, smem);
     if (e != cudaSuccess) return e;
-    select_compact_kernel<<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, margin, thr, needed_cap);
+    select_compact_kernel<<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, fixed_count, margin, thr, needed_cap);
     return cudaGetLastError();
 }
 
@@ -224,12 +278,12 @@ cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt
     if (exact) {
         e = set_smem(final_kernel<true>, smem);
         if (e != cudaSuccess) return e;
-        final_kernel<true><<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset, out_idx,
+        final_kernel<true><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset, out_idx,
                                                             out_score, out_score64, needed_cap);
     } else {
         e = set_smem(final_kernel<false>, smem);
         if (e != cudaSuccess) return e;
-        final_kernel<false><<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
+        final_kernel<false><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
                                                              out_idx, out_score, out_score64, needed_cap);
     }
     return cudaGetLastError();
