@@ -71,6 +71,7 @@ struct hwer_index {
     unsigned int* cnt = nullptr;
     float* thr = nullptr;
     float* margin = nullptr;
+    float* floor = nullptr;
     size_t ws_queries = 0, ws_cap = 0;
     unsigned int* needed_dev = nullptr;
     unsigned int* needed_host = nullptr;   // pinned
@@ -91,6 +92,8 @@ int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
     if (ix->cnt) cudaFree(ix->cnt);
     if (ix->thr) cudaFree(ix->thr);
     if (ix->margin) cudaFree(ix->margin);
+    if (ix->floor) cudaFree(ix->floor);
+    ix->floor = nullptr;
     ix->cand = nullptr; ix->cnt = nullptr; ix->thr = nullptr; ix->margin = nullptr;
     ix->ws_queries = ix->ws_cap = 0;
     const size_t q = queries > ix->ws_queries ? queries : ix->ws_queries;
@@ -98,7 +101,8 @@ int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
     if (cudaMalloc(&ix->cand, q * c * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ix->cnt, q * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&ix->thr, q * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&ix->margin, q * sizeof(float)) != cudaSuccess) {
+        cudaMalloc(&ix->margin, q * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&ix->floor, q * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
         return fail(HWER_E_NOMEM, "hwer_topk: cannot allocate the candidate workspace");
     }
@@ -246,6 +250,7 @@ int hwer_index_destroy(hwer_index_t* ix) {
     if (ix->cnt) cudaFree(ix->cnt);
     if (ix->thr) cudaFree(ix->thr);
     if (ix->margin) cudaFree(ix->margin);
+    if (ix->floor) cudaFree(ix->floor);
     if (ix->needed_dev) cudaFree(ix->needed_dev);
     if (ix->needed_host) cudaFreeHost(ix->needed_host);
     for (auto& e : ix->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -287,13 +292,10 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         const float* Q = queries_dev + (size_t)q0 * ix->d;
         HWER_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(unsigned int) * Bc, stream));
         HWER_CUDA(hwer::launch_fill_f32(ix->thr, Bc, -INFINITY, stream));
-        const float* margin = nullptr;
-        if (exact || !ix->use_tc) {
-            // the CUDA-core path scores in fp32: its (tiny) margin keeps even bf16-less indexes exact
-            HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->margin, stream));
-            margin = ix->margin;
-        }
-        ix->other_launches += margin ? 3 : 2;   // fill + (margin) + final
+        // the CUDA-core path scores in fp32: its (tiny) margin keeps even bf16-less indexes exact
+        const float* margin = (exact || !ix->use_tc) ? ix->margin : nullptr;
+        HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->max_norm, ix->margin, ix->floor, stream));
+        ix->other_launches += 3;   // fill + margin/floor + final
         long long seen = 0;
         int round = 0;
         while (seen < T) {
@@ -309,7 +311,7 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
                 if (nq > nq_max) nq = nq_max;
                 p.nq = nq; p.nqb = (Bc + nq - 1) / nq;
-                p.thr = ix->thr; p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
+                p.thr = ix->thr; p.floor = ix->floor; p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
                 p.n_items = ix->n; p.tile_begin = (int)seen; p.tile_end = (int)end;
                 p.tile_mul = ix->tile_mul; p.tile_mod = T;
                 p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics

@@ -65,14 +65,16 @@ blend_normalize_vec_kernel(const float* __restrict__ content, const float* __res
         if (HAS_C) {
             const float nc = sqrtf(warp_sum(sc));
             const float a = alpha_rows ? alpha_rows[row] : alpha;
-            const float b = 1.0f - a;
+            // unit() of each source first, as the spec composes them; the two inner normalisations use one
+            // reciprocal per row (an IEEE divide per element made this kernel instruction-bound), the final
+            // one below stays a true division like numpy's
+            const float wc = a * (1.0f / nc), wg = (1.0f - a) * (1.0f / ng);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                // unit() of each source first, exactly as the spec composes them
-                g[i].x = a * (c[i].x / nc) + b * (g[i].x / ng);
-                g[i].y = a * (c[i].y / nc) + b * (g[i].y / ng);
-                g[i].z = a * (c[i].z / nc) + b * (g[i].z / ng);
-                g[i].w = a * (c[i].w / nc) + b * (g[i].w / ng);
+                g[i].x = fmaf(wc, c[i].x, wg * g[i].x);
+                g[i].y = fmaf(wc, c[i].y, wg * g[i].y);
+                g[i].z = fmaf(wc, c[i].z, wg * g[i].z);
+                g[i].w = fmaf(wc, c[i].w, wg * g[i].w);
                 sv = fmaf(g[i].x, g[i].x, sv); sv = fmaf(g[i].y, g[i].y, sv);
                 sv = fmaf(g[i].z, g[i].z, sv); sv = fmaf(g[i].w, g[i].w, sv);
             }

@@ -92,10 +92,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)   // suspend-time hint (ns): sleep, do not spin
         : "memory");
     return ok != 0;
 }
@@ -170,6 +170,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= uint64_t(1024 >> 4) << 32;    // SBO: 8 rows x 128 B between row groups
     d |= uint64_t(1) << 46;            // descriptor version (Blackwell)
     d |= uint64_t(2) << 61;            // SWIZZLE_128B
+    return d;
+}
+
+// K-major operand without swizzle, K = 16 bf16 (32 B) per row: 8-row x 16-byte core matrices of 128 B; the two
+// core matrices along K are LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart
+// (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO)) of cute's make_umma_desc<Major::K>, SWIZZLE_NONE = 0).
+__device__ __forceinline__ uint64_t umma_desc_k_noswizzle(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFFu);
+    d |= uint64_t(128 >> 4) << 16;     // LBO
+    d |= uint64_t(256 >> 4) << 32;     // SBO
+    d |= uint64_t(1) << 46;            // descriptor version (Blackwell)
     return d;
 }
 

@@ -30,6 +30,7 @@ struct FilterParams {
     int slots;                // CTAs cooperating on one query block (split of the item tiles)
     int qb_step;              // query blocks advanced per outer iteration (= gridDim.x / slots)
     const float* thr;         // [B] current per-query admission threshold
+    const float* floor;       // [B] finite lower bound of any score of the query (stands in for thr = -inf)
     unsigned long long* cand; // [B, cap] packed candidate keys
     unsigned int* cnt;        // [B] candidate counters (may exceed cap => overflow)
     unsigned int cap;
@@ -37,6 +38,7 @@ struct FilterParams {
     int tile_begin, tile_end; // item-tile range of this round (positions in the visiting order)
     long long tile_mul;       // visiting order: physical tile = (position * tile_mul) % tile_mod
     long long tile_mod;
+    long long tile_step;      // (slots * tile_mul) % tile_mod: visiting-order stride of one CTA
     int stages;               // smem pipeline depth
     int acc_stages;           // TMEM accumulator stages
     int tmem_cols;            // power of two >= acc_stages * nq
@@ -55,8 +57,8 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
                                const float* thr, unsigned long long* cand, unsigned int* cnt, unsigned int cap,
                                long long row_begin, long long row_end, int num_sms, cudaStream_t stream);
 
-cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float* margin,
-                                cudaStream_t stream);
+cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float max_norm, float* margin,
+                                float* floor, cudaStream_t stream);
 cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream);
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,

@@ -26,6 +26,7 @@ constexpr int kSlabBytes = kTileItems * 128;  // one 64-wide K block of an item 
 constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant, splitting the query columns
 constexpr int kThreadsTc = (2 + kEpiWarps) * 32;
 constexpr int kHitQueue = 64;                 // per-warp shared-memory hit queue (entries)
+constexpr int kBiasRowBytes = 32;             // K=16 bf16 per row of the threshold-MMA operands
 
 enum : int { kModeFilter = 0, kModeDump = 1, kModeDense = 2 };
 
@@ -77,26 +78,11 @@ struct HitQueue {
     }
 };
 
-// 1 if any of eight scores reaches its threshold (NaN never does).
-__device__ __forceinline__ uint32_t any_ge8(const uint32_t* v, const float* t) {
-    uint32_t r;
-    asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.ge.f32 p, %1, %9;\n\t"
-        "setp.ge.f32 q, %2, %10;\n\t"
-        "setp.ge.or.f32 p, %3, %11, p;\n\t"
-        "setp.ge.or.f32 q, %4, %12, q;\n\t"
-        "setp.ge.or.f32 p, %5, %13, p;\n\t"
-        "setp.ge.or.f32 q, %6, %14, q;\n\t"
-        "setp.ge.or.f32 p, %7, %15, p;\n\t"
-        "setp.ge.or.f32 q, %8, %16, q;\n\t"
-        "or.pred p, p, q;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(r)
-        : "f"(__uint_as_float(v[0])), "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[2])),
-          "f"(__uint_as_float(v[3])), "f"(__uint_as_float(v[4])), "f"(__uint_as_float(v[5])),
-          "f"(__uint_as_float(v[6])), "f"(__uint_as_float(v[7])), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]),
-          "f"(t[4]), "f"(t[5]), "f"(t[6]), "f"(t[7]));
-    return r;
+// The filter rounds fold the threshold into the MMA: one extra K=16 step multiplies a constant-ones slab with
+// (-thr_hi, -thr_lo), so the accumulator already holds score - thr and "is any of these 8 scores admissible"
+// is "is any sign bit clear": the bitwise AND of the eight words keeps the sign bit only if all are negative.
+__device__ __forceinline__ uint32_t and8(const uint32_t* v) {
+    return (v[0] & v[1] & v[2]) & (v[3] & v[4] & v[5]) & (v[6] & v[7]);
 }
 
 // Compare W accumulator columns of one catalogue row against the thresholds of the W queries they belong to.
@@ -125,29 +111,22 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const flo
         }
         return;
     }
-    float t[W];
-    const float4* t4 = reinterpret_cast<const float4*>(thr_s + c0);
-#pragma unroll
-    for (int j = 0; j < W / 4; ++j) {
-        float4 x = t4[j];
-        t[4 * j + 0] = x.x; t[4 * j + 1] = x.y; t[4 * j + 2] = x.z; t[4 * j + 3] = x.w;
-    }
-    // Eight columns per asm block, two predicate chains per block, blocks independent: the serial
-    // FSETP...OR chain NVVM would otherwise build is issue-latency bound (ncu: "wait" stalls dominate).
     uint32_t grp[W / 8];
 #pragma unroll
-    for (int g = 0; g < W / 8; ++g) grp[g] = any_ge8(&v[8 * g], &t[8 * g]);
-    uint32_t anyw = 0;
+    for (int g = 0; g < W / 8; ++g) grp[g] = and8(&v[8 * g]);
+    uint32_t all = grp[0];
 #pragma unroll
-    for (int g = 0; g < W / 8; ++g) anyw |= grp[g];
-    if (__any_sync(0xffffffffu, anyw && row_ok)) {          // warp-uniform from here on: no divergence
+    for (int g = 1; g < W / 8; ++g) all &= grp[g];
+    if (__any_sync(0xffffffffu, (int)all >= 0 && row_ok)) {     // warp-uniform from here on: no divergence
 #pragma unroll
         for (int g = 0; g < W / 8; ++g) {
-            if (__any_sync(0xffffffffu, grp[g] && row_ok)) {
+            if (__any_sync(0xffffffffu, (int)grp[g] >= 0 && row_ok)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float s = __uint_as_float(v[8 * g + j]);
-                    hq.push((s >= t[8 * g + j]) & row_ok, s, (uint32_t)row, q_base + c0 + 8 * g + j, p, lane);
+                    const float diff = __uint_as_float(v[8 * g + j]);            // score - thr (NaN stays NaN)
+                    // the key carries score = diff + thr: one fp32 rounding (~3e-8), far inside the margin
+                    hq.push((diff >= 0.0f) & row_ok, diff + thr_s[c0 + 8 * g + j], (uint32_t)row,
+                            q_base + c0 + 8 * g + j, p, lane);
                 }
             }
         }
@@ -158,8 +137,9 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams p) {
     extern __shared__ uint8_t smem_raw[];
-    // 128B-swizzled operands need 1024-byte aligned slabs.
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 128B-swizzled operands need 1024-byte aligned slabs.  Pointer arithmetic on the __shared__ array (not a
+    // round trip through an integer) keeps the shared address space visible to the compiler: LDS/STS, not LD/ST.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int nq = p.nq;
     const int kb = p.kb;
@@ -168,7 +148,9 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
 
     uint8_t* q_smem = smem;
     uint8_t* item_smem = q_smem + kb * q_slab;   // kb*q_slab is a multiple of 1024 (nq % 8 == 0)
-    float* thr_s = reinterpret_cast<float*>(item_smem + (size_t)p.stages * stage_bytes);
+    uint8_t* ones_smem = item_smem + (size_t)p.stages * stage_bytes;   // [128 rows x K16] constant (1, 1, 0, ...)
+    uint8_t* bias_smem = ones_smem + kBiasRowBytes * kTileItems;       // [nq rows x K16] (-thr_hi, -thr_lo, 0, ...)
+    float* thr_s = reinterpret_cast<float*>(bias_smem + kBiasRowBytes * kMaxNQ);
     uint4* hitq_s = reinterpret_cast<uint4*>(thr_s + kMaxNQ);                   // [kEpiWarps][kHitQueue]
     uint64_t* bars = reinterpret_cast<uint64_t*>(hitq_s + kEpiWarps * kHitQueue);
     uint64_t* full_bar = bars;                            // [stages]   TMA -> MMA
@@ -195,6 +177,15 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     if (warp == 1) {
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         tmem_relinquish();
+    }
+    if (MODE == kModeFilter) {
+        // constant A operand of the threshold MMA: K-major, no swizzle, 8-row core matrices of 128 B;
+        // row r, columns 0..7 live at (r/8)*256 + (r%8)*16, columns 8..15 (all zero) 128 B further
+        for (int i = threadIdx.x; i < kTileItems * 2; i += kThreadsTc) {
+            const int r = i >> 1, half = i & 1;
+            const uint4 val = half ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 (1, 1)
+            *reinterpret_cast<uint4*>(ones_smem + (r >> 3) * 256 + half * 128 + (r & 7) * 16) = val;
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -240,7 +231,27 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             }
             for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
                 const int q = q_base + i;
-                thr_s[i] = (q < p.B) ? (MODE == kModeFilter ? p.thr[q] : 0.0f) : __int_as_float(0x7f800000);
+                if (MODE == kModeFilter) {
+                    // thr ~ hi + lo with both parts bf16 and hi + lo <= thr (lo rounds toward -inf), so folding
+                    // it into the MMA only ever admits more; "no threshold yet" (-inf) becomes the query's floor
+                    float t = __int_as_float(0x7f800000);            // padded query: +huge, never admits
+                    if (q < p.B) t = fmaxf(p.thr[q], p.floor[q]);
+                    t = fminf(t, 3.0e38f);
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+                    const float rem = t - __bfloat162float(hi);
+                    uint32_t u = __float_as_uint(rem);
+                    uint32_t lo_bits = u & 0xFFFF0000u;
+                    if ((u & 0x80000000u) && (u & 0xFFFFu)) lo_bits += 0x10000u;     // negative: away from zero
+                    const float lo = __uint_as_float(lo_bits);
+                    thr_s[i] = __bfloat162float(hi) + lo;                        // what the MMA subtracts
+                    const uint32_t nhi = (uint32_t)(__bfloat16_as_ushort(hi) ^ 0x8000u);
+                    const uint32_t nlo = (lo_bits >> 16) ^ 0x8000u;
+                    uint8_t* dst = bias_smem + (i >> 3) * 256 + (i & 7) * 16;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(nhi | (nlo << 16), 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    thr_s[i] = 0.0f;
+                }
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
         }
@@ -249,11 +260,14 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         if (warp == 0) {
             // ===================== TMA producer =====================
             if (lane == 0) {
+                long long phys = ((long long)(p.tile_begin + slot) * p.tile_mul) % p.tile_mod;
                 for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                     uint8_t* dst = item_smem + (size_t)stage * stage_bytes;
-                    const int tile_row = (int)(((long long)t * p.tile_mul) % p.tile_mod) * kTileItems;
+                    const int tile_row = (int)phys * kTileItems;
+                    phys += p.tile_step;                       // (slots * tile_mul) % tile_mod, from the host
+                    if (phys >= p.tile_mod) phys -= p.tile_mod;
                     for (int k = 0; k < kb; ++k)
                         tma_load_2d(dst + k * kSlabBytes, &tmap, k * kKBlock, tile_row, &full_bar[stage], policy);
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -279,6 +293,9 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                             umma_bf16(d_tmem, adesc, bdesc, idesc, (k | s) ? 1u : 0u);
                         }
                     }
+                    if (MODE == kModeFilter)        // accumulator -= thr (see epilogue_chunk)
+                        umma_bf16(d_tmem, umma_desc_k_noswizzle(smem_u32(ones_smem)),
+                                  umma_desc_k_noswizzle(smem_u32(bias_smem)), idesc, 1u);
                     umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
                     umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -294,6 +311,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             HitQueue hq;
             hq.slots = hitq_s + e * kHitQueue;
             hq.count = 0;
+            long long phys = ((long long)(p.tile_begin + slot) * p.tile_mul) % p.tile_mod;
             for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
                 // deferred appends of the previous tile's hits: issue the slot-allocating atomics now ...
                 int pend = 0;
@@ -317,7 +335,9 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after_sync();
                 const long long tile_pos = t - p.tile_begin;
-                const long long row = (((long long)t * p.tile_mul) % p.tile_mod) * kTileItems + quad * 32 + lane;
+                const long long row = phys * kTileItems + quad * 32 + lane;
+                phys += p.tile_step;
+                if (phys >= p.tile_mod) phys -= p.tile_mod;
                 const bool row_ok = row < p.n_items;
                 const long long dense_pos = tile_pos * kTileItems + quad * 32 + lane;
                 const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * (uint32_t)nq;
@@ -396,8 +416,8 @@ score_filter_simt_kernel(const float* __restrict__ table, long long n_items, int
     }
 }
 
-__global__ void query_margin_kernel(const float* __restrict__ queries, int B, int d, float factor,
-                                    float* __restrict__ margin) {
+__global__ void query_margin_kernel(const float* __restrict__ queries, int B, int d, float factor, float max_norm,
+                                    float* __restrict__ margin, float* __restrict__ floor) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= B) return;
     float s = 0.0f;
@@ -406,8 +426,12 @@ __global__ void query_margin_kernel(const float* __restrict__ queries, int B, in
         s = fmaf(v, v, s);
     }
     s = warp_sum(s);
-    // round the norm up a little: the bound must never be under-estimated
-    if (lane_id() == 0) margin[q] = factor * sqrtf(s) * 1.0001f;
+    if (lane_id() == 0) {
+        const float nrm = sqrtf(s) * 1.0001f;       // rounded up: the bounds must never be under-estimated
+        if (margin) margin[q] = factor * nrm;
+        // no score of this query can be below -|q| * max|x| (minus the bf16 slack): a finite "-inf"
+        floor[q] = -(1.01f * nrm * max_norm + 1e-30f);
+    }
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
@@ -419,7 +443,8 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
 
 size_t filter_tc_smem_bytes(int nq, int kb, int stages) {
     return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + kMaxNQ * sizeof(float) +
-           (size_t)kEpiWarps * kHitQueue * sizeof(uint4) + (2 * stages + 8) * sizeof(uint64_t) + 16;
+           (size_t)kBiasRowBytes * (kTileItems + kMaxNQ) + (size_t)kEpiWarps * kHitQueue * sizeof(uint4) +
+           (2 * stages + 8) * sizeof(uint64_t) + 16;
 }
 
 int filter_tc_pick_stages(int nq, int kb) {
@@ -450,6 +475,7 @@ cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sm
         grid = num_sms;
     }
     p.stream_once = (p.nqb == 1) ? 1 : 0;
+    p.tile_step = ((long long)p.slots * p.tile_mul) % p.tile_mod;
     const size_t smem = filter_tc_smem_bytes(p.nq, p.kb, p.stages);
     static bool attr_done = false;   // the opt-in shared-memory ceiling is a per-function, per-process setting
     if (!attr_done) {
@@ -484,10 +510,10 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float* margin,
-                                cudaStream_t stream) {
+cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float max_norm, float* margin,
+                                float* floor, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, margin);
+    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, max_norm, margin, floor);
     return cudaGetLastError();
 }
 
