@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -126,7 +127,8 @@ void prof_end(hwer_index* ix, cudaStream_t stream, bool began) {
 }
 
 struct Schedule {
-    int growth;
+    int growth;             // early rounds: score `growth` x the rows seen so far
+    long long late_tiles;   // once this many tiles have been seen, rounds only double (growth 1)
     unsigned int cap;
     long long first_tiles;
 };
@@ -139,8 +141,9 @@ int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
     if (first_rows < 2LL * k) first_rows = 2LL * k;
     s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
     first_rows = s->first_tiles * hwer::kTileItems;
-    int g = (B <= 256) ? 16 : 8;
+    int g = (B <= 16) ? 32 : 8;            // measured on the C4 table (scripts/tune_schedule.py)
     while (g > 2 && 3LL * k * g > max_cap) g >>= 1;
+    if (const char* e = getenv("HWER_GROWTH")) { int v = atoi(e); if (v >= 1 && 3LL * k * v <= max_cap) g = v; }   // tuning knob
     unsigned long long want = 3ULL * k * g;
     if (want < (unsigned long long)first_rows) want = first_rows;
     if (cap_user) {
@@ -151,6 +154,11 @@ int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
     while (cap < want) cap <<= 1;
     if (cap > max_cap) return fail(HWER_E_INVALID, "hwer_topk: k (or cap) too large for the shared-memory selector");
     s->growth = g;
+    // A round admits ~k * growth * 1.4 candidates per query however long it is, i.e. a hit rate of
+    // 1.4 k / rows_seen_before: in the rounds that dominate the run time the thresholds are refreshed by doubling.
+    // (tiny batches have too few hits to care and would only pay for the extra launches)
+    s->late_tiles = B <= 16 ? (1LL << 40) : (B <= 128 ? (1024 * 1024) : (256 * 1024)) / hwer::kTileItems;
+    if (const char* e = getenv("HWER_LATE_ROWS")) s->late_tiles = atoll(e) / hwer::kTileItems;   // tuning knob
     s->cap = (unsigned int)cap;
     return HWER_OK;
 }
@@ -299,7 +307,7 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         long long seen = 0;
         int round = 0;
         while (seen < T) {
-            long long take = round == 0 ? sch.first_tiles : seen * sch.growth;
+            long long take = round == 0 ? sch.first_tiles : seen * (seen >= sch.late_tiles ? 1 : sch.growth);
             long long end = seen + take;
             if (end > T || (T - end) * 4 < take) end = T;
             const bool timed = prof_begin(ix, stream);

@@ -14,7 +14,7 @@
 //   UMMA N = nq <= 256 queries   (B operand: resident in shared memory for the CTA's lifetime)
 //   UMMA K = 16, d_pad/16 steps  (accumulators: fp32 in TMEM, acc_stages-deep)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
-// warps 2..5 = epilogue (tcgen05.ld -> threshold compare -> rare append).
+// warps 2..17 = epilogue (tcgen05.ld -> sign test of score - thr -> rare append).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,9 +23,11 @@ namespace hwer {
 namespace {
 
 constexpr int kSlabBytes = kTileItems * 128;  // one 64-wide K block of an item tile: 16 KB
-constexpr int kEpiWarps = 8;                  // two per TMEM lane quadrant, splitting the query columns
+constexpr int kEpiWarps = 16;                 // four per TMEM lane quadrant (one SM scheduler each), splitting the
+                                              // query columns: the epilogue is latency-, not issue-bound
 constexpr int kThreadsTc = (2 + kEpiWarps) * 32;
 constexpr int kHitQueue = 64;                 // per-warp shared-memory hit queue (entries)
+constexpr int kColParts = kEpiWarps / 4;      // warps sharing a lane quadrant
 constexpr int kBiasRowBytes = 32;             // K=16 bf16 per row of the threshold-MMA operands
 
 enum : int { kModeFilter = 0, kModeDump = 1, kModeDense = 2 };
@@ -161,6 +163,8 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // epilogue warps that own at least one column chunk of this query-block width (narrow blocks: fewer warps)
+    const int parts_active = (nq + 31) / 32 < kColParts ? (nq + 31) / 32 : kColParts;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
@@ -170,7 +174,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         }
         for (int i = 0; i < p.acc_stages; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEpiWarps);   // one arrival per epilogue warp
+            mbar_init(&tempty_bar[i], 4 * parts_active);   // one arrival per participating epilogue warp
         }
         fence_mbar_init();
     }
@@ -303,11 +307,11 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 }
             }
             __syncwarp();
-        } else {
-            // ===================== epilogue (8 warps) =====================
+        } else if (((warp - 2) >> 2) < parts_active) {
+            // ===================== epilogue (up to 16 warps) =====================
             const int e = warp - 2;
             const uint32_t quad = (uint32_t)warp & 3u;   // TMEM lane quadrant this warp may read
-            const int half = e >> 2;                      // which half of the 32-column chunks this warp takes
+            const int part = e >> 2;                      // which of the interleaved 32-column chunks it takes
             HitQueue hq;
             hq.slots = hitq_s + e * kHitQueue;
             hq.count = 0;
@@ -341,14 +345,14 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 const bool row_ok = row < p.n_items;
                 const long long dense_pos = tile_pos * kTileItems + quad * 32 + lane;
                 const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * (uint32_t)nq;
-                int c0 = 32 * half;
-                for (; c0 + 32 <= nq; c0 += 64) {
+                int c0 = 32 * part;
+                for (; c0 + 32 <= nq; c0 += 32 * kColParts) {
                     uint32_t v[32];
                     tmem_ld_x32(taddr + c0, v);
                     tmem_ld_wait();
                     epilogue_chunk<32, MODE>(v, thr_s, c0, q_base, row, row_ok, p, hq, lane, dense_pos);
                 }
-                if (c0 < nq && c0 + 16 == nq) {          // a trailing 16-column chunk belongs to exactly one half
+                if (c0 < nq && c0 + 16 == nq) {          // a trailing 16-column chunk belongs to exactly one part
                     uint32_t v[16];
                     tmem_ld_x16(taddr + c0, v);
                     tmem_ld_wait();
