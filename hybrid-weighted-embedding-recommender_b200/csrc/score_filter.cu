@@ -280,31 +280,41 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             __syncwarp();
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
-            if (lane == 0) {
-                const uint32_t q_addr = smem_u32(q_smem);
-                const uint32_t i_addr = smem_u32(item_smem);
-                for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
-                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + acc * (uint32_t)nq;
-                    const uint32_t a_base = i_addr + stage * (uint32_t)stage_bytes;
-                    for (int k = 0; k < kb; ++k) {
+            // The whole warp walks the loop converged, so ring positions and descriptor halves stay in uniform
+            // registers; only the issue itself is predicated on the elected lane.  (Run by lane 0 alone, every
+            // operand took an ELECT + R2UR round trip: ~35 instructions per MMA, and the single issuing thread,
+            // not the tensor pipe, set the pace -- profiles/README.md, v4 -> v5.)
+            const bool leader = elect_one();
+            const uint32_t sw_hi = (uint32_t)(umma_desc_k_sw128(0) >> 32);
+            const uint32_t ns_hi = (uint32_t)(umma_desc_k_noswizzle(0) >> 32);
+            const uint32_t q_lo = (uint32_t)umma_desc_k_sw128(smem_u32(q_smem));
+            const uint32_t i_lo = (uint32_t)umma_desc_k_sw128(smem_u32(item_smem));
+            const uint32_t ones_lo = (uint32_t)umma_desc_k_noswizzle(smem_u32(ones_smem));
+            const uint32_t bias_lo = (uint32_t)umma_desc_k_noswizzle(smem_u32(bias_smem));
+            const uint32_t stage_step = (uint32_t)stage_bytes >> 4;     // descriptor address units are 16 bytes
+            const uint32_t q_step = (uint32_t)q_slab >> 4;
+            for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)nq;
+                uint32_t a_lo = i_lo + stage * stage_step;
+                uint32_t b_lo = q_lo;
+                for (int k = 0; k < kb; ++k) {
 #pragma unroll
-                        for (int s = 0; s < kKBlock / 16; ++s) {
-                            const uint64_t adesc = umma_desc_k_sw128(a_base + k * kSlabBytes + s * 32);
-                            const uint64_t bdesc = umma_desc_k_sw128(q_addr + k * q_slab + s * 32);
-                            umma_bf16(d_tmem, adesc, bdesc, idesc, (k | s) ? 1u : 0u);
-                        }
-                    }
+                    for (int s = 0; s < kKBlock / 16; ++s)
+                        if (leader) umma_bf16_lohi(d_tmem, a_lo + 2 * s, sw_hi, b_lo + 2 * s, sw_hi, idesc, (k | s) ? 1u : 0u);
+                    a_lo += kSlabBytes >> 4;
+                    b_lo += q_step;
+                }
+                if (leader) {
                     if (MODE == kModeFilter)        // accumulator -= thr (see epilogue_chunk)
-                        umma_bf16(d_tmem, umma_desc_k_noswizzle(smem_u32(ones_smem)),
-                                  umma_desc_k_noswizzle(smem_u32(bias_smem)), idesc, 1u);
+                        umma_bf16_lohi(d_tmem, ones_lo, ns_hi, bias_lo, ns_hi, idesc, 1u);
                     umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
                     umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
-                    if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
                 }
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+                if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
             __syncwarp();
         } else if (((warp - 2) >> 2) < parts_active) {
