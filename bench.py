@@ -67,7 +67,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                          "-lms", "20", "-i", str(gpu_index)], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -324,9 +324,10 @@ def run_b200(a):
     # ---- headline: device-resident throughput (events on the launching stream), clocks sampled meanwhile
     sampler = ClockSampler(local) if rank == 0 else None
     ms, _, _, _, out = measure(a.batch, a.steps, a.warmup, profile=False)
-    clocks = sampler.stop() if sampler else None
     # same steps again with the filter kernel bracketed by events: kernel time for the roofline + launch counts
+    # (the clock sampler keeps running: both passes are the same work, and one pass can be shorter than a sample)
     pms, filt_ms, filt_l, other_l, _ = measure(a.batch, a.steps, 1, profile=True)
+    clocks = sampler.stop() if sampler else None
     launches_per_step = (filt_l + other_l) / a.steps + (1 if world > 1 else 0)
     roof = roofline(a.batch, filt_ms / a.steps)
     roof["share_of_step"] = (filt_ms / a.steps) / (pms / a.steps)

@@ -133,16 +133,20 @@ struct Schedule {
     long long first_tiles;
 };
 
-// Round schedule: round 0 scores `first_tiles` tiles with an open threshold; each later round scores
-// `growth` times what has been seen, so it admits about k * growth candidates per query.
+// Round schedule: round 0 scores `first_tiles` tiles densely (open threshold, positional writes); each later round
+// scores `growth` times what has been seen, so it admits about 1.4 * k * growth candidates per query however long it
+// is (DESIGN.md "Rounds").  A hit costs the epilogue far more than a miss, a round costs a launch plus a
+// select_compact pass, and both scale differently with the batch: the table below is measured on the C4 catalogue
+// (scripts/tune_schedule.py, profiles/r01_v6_tune.txt).
 int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
     const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
-    long long first_rows = 1024;
+    long long first_rows = B > 512 ? 4096 : 8192;
+    int g = B <= 16 ? 32 : (B <= 128 ? 8 : (B <= 512 ? 4 : 2));
     if (first_rows < 2LL * k) first_rows = 2LL * k;
+    if (const char* e = getenv("HWER_FIRST_ROWS")) { long long v = atoll(e); if (v >= 2LL * k && v <= max_cap) first_rows = v; }   // tuning knob
     s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
     first_rows = s->first_tiles * hwer::kTileItems;
-    int g = (B <= 16) ? 32 : 8;            // measured on the C4 table (scripts/tune_schedule.py)
-    while (g > 2 && 3LL * k * g > max_cap) g >>= 1;
+    while (g > 1 && 3LL * k * g > max_cap) g >>= 1;
     if (const char* e = getenv("HWER_GROWTH")) { int v = atoi(e); if (v >= 1 && 3LL * k * v <= max_cap) g = v; }   // tuning knob
     unsigned long long want = 3ULL * k * g;
     if (want < (unsigned long long)first_rows) want = first_rows;
@@ -154,10 +158,7 @@ int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
     while (cap < want) cap <<= 1;
     if (cap > max_cap) return fail(HWER_E_INVALID, "hwer_topk: k (or cap) too large for the shared-memory selector");
     s->growth = g;
-    // A round admits ~k * growth * 1.4 candidates per query however long it is, i.e. a hit rate of
-    // 1.4 k / rows_seen_before: in the rounds that dominate the run time the thresholds are refreshed by doubling.
-    // (tiny batches have too few hits to care and would only pay for the extra launches)
-    s->late_tiles = B <= 16 ? (1LL << 40) : (B <= 128 ? (1024 * 1024) : (256 * 1024)) / hwer::kTileItems;
+    s->late_tiles = 1LL << 40;            // optional switch to plain doubling once this many tiles have been seen
     if (const char* e = getenv("HWER_LATE_ROWS")) s->late_tiles = atoll(e) / hwer::kTileItems;   // tuning knob
     s->cap = (unsigned int)cap;
     return HWER_OK;
@@ -315,7 +316,7 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 hwer::FilterParams p;
                 memset(&p, 0, sizeof p);
                 p.queries = Q; p.B = Bc; p.d = ix->d; p.kb = ix->d_pad / 64;
-                int nq = (Bc + 15) / 16 * 16;
+                int nq = (Bc + 31) / 32 * 32;     // whole 32-column epilogue chunks
                 const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
                 if (nq > nq_max) nq = nq_max;
                 p.nq = nq; p.nqb = (Bc + nq - 1) / nq;
@@ -399,7 +400,7 @@ int hwer_debug_scores(hwer_index_t* ix, const float* queries_dev, int32_t B, flo
     hwer::FilterParams p;
     memset(&p, 0, sizeof p);
     p.queries = queries_dev; p.B = B; p.d = ix->d; p.kb = ix->d_pad / 64;
-    int nq = (B + 15) / 16 * 16;
+    int nq = (B + 31) / 32 * 32;
     const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
     if (nq > nq_max) nq = nq_max;
     p.nq = nq; p.nqb = (B + nq - 1) / nq;

@@ -25,7 +25,7 @@ struct FilterParams {
     int B;
     int d;                    // logical embedding width
     int kb;                   // d_pad / 64
-    int nq;                   // queries per block (multiple of 16, <= 256)
+    int nq;                   // queries per block (multiple of 32, <= 256)
     int nqb;                  // number of query blocks = ceil(B / nq)
     int slots;                // CTAs cooperating on one query block (split of the item tiles)
     int qb_step;              // query blocks advanced per outer iteration (= gridDim.x / slots)

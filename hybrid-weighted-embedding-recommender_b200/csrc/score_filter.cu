@@ -14,7 +14,7 @@
 //   UMMA N = nq <= 256 queries   (B operand: resident in shared memory for the CTA's lifetime)
 //   UMMA K = 16, d_pad/16 steps  (accumulators: fp32 in TMEM, acc_stages-deep)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
-// warps 2..17 = epilogue (tcgen05.ld -> sign test of score - thr -> rare append).
+// warps 2..17 = epilogue (tcgen05.ld -> release the accumulator -> sign test of score - thr -> rare append).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -38,47 +38,50 @@ __device__ __forceinline__ void append_candidate(unsigned long long* cand, unsig
     if (slot < cap) cand[(size_t)q * cap + slot] = make_key(s, row);
 }
 
-// Per-warp hit queue.  Hits are rare (DESIGN.md "hit rate"), so the epilogue only parks them in shared memory
-// with warp-uniform ballots; the global atomicAdd that allocates a slot in the query's candidate list is issued
-// at the start of the NEXT tile and its result is consumed at that tile's end, so the ~1 us L2 round trip
-// overlaps a whole tile of compare work instead of stalling the warp.
-// Out of line on purpose: it is expanded at 32+ call sites otherwise and the epilogue outgrows the I-cache.
-__device__ __noinline__ void hit_queue_flush(const uint4* slots, int count, unsigned long long* cand,
-                                             unsigned int* cnt, unsigned int cap) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    for (int base = 0; base < count; base += 32) {
-        if (base + lane < count) {
-            const uint4 e = slots[base + lane];
-            const unsigned int slot = atomicAdd(&cnt[e.z], 1u);
-            if (slot < cap) cand[(size_t)e.z * cap + slot] = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
-        }
-    }
-    __syncwarp();
+// Per-warp hit queue in shared memory.  Hits are rare (DESIGN.md "hit rate"): a lane that finds one parks it here
+// with a shared-memory atomic; the global atomicAdd that allocates the slot in the query's candidate list is
+// issued by the whole warp at the start of the NEXT tile and its result consumed at that tile's end, so the ~1 us
+// L2 round trip overlaps a tile of work instead of stalling the warp.
+struct HitCtx {
+    uint32_t slots;               // shared-space address of [kHitQueue] x {key lo, key hi, query, -}
+    uint32_t count;               // shared-space address of the number of entries parked since the last drain
+                                  // (may exceed kHitQueue: the overflow was appended directly)
+};
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
 }
 
-struct HitQueue {
-    uint4* slots;     // [kHitQueue] {key lo, key hi, query, -}
-    int count;        // warp-uniform
-
-    __device__ __forceinline__ void flush_blocking(const FilterParams& p, int lane) {
-        (void)lane;
-        hit_queue_flush(slots, count, p.cand, p.cnt, p.cap);
-        count = 0;
+// Out of line on purpose: 64 call sites per epilogue warp, executed by the odd lane only.  Everything is passed in
+// registers and the queue is addressed in the shared window (ATOMS/STS, not generic atomics).
+__device__ __noinline__ void push_hit(uint32_t slots, uint32_t count, const FilterParams* p, float score,
+                                      uint32_t row, int q) {
+    uint32_t s;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(s) : "r"(count) : "memory");
+    const unsigned long long k = make_key(score, row);
+    if (s < (uint32_t)kHitQueue) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slots + s * 16u), "r"((uint32_t)k),
+                     "r"((uint32_t)(k >> 32)), "r"((uint32_t)q), "r"(0u)
+                     : "memory");
+    } else {                        // queue full (only the hit-dense first rounds): append directly
+        const unsigned int slot = atomicAdd(&p->cnt[q], 1u);
+        if (slot < p->cap) p->cand[(size_t)q * p->cap + slot] = k;
     }
-    // one query column: `hit` lanes park their (score, row); at most 32 entries
-    __device__ __forceinline__ void push(bool hit, float s, uint32_t row, int q, const FilterParams& p, int lane) {
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            if (count + 32 > kHitQueue) flush_blocking(p, lane);
-            if (hit) {
-                const unsigned long long k = make_key(s, row);
-                slots[count + __popc(m & ((1u << lane) - 1u))] = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)q, 0u);
-            }
-            count += __popc(m);
+}
+
+// Blocking drain of queue entries [begin, end) by the whole warp.
+__device__ __noinline__ void hit_queue_flush(uint32_t slots, const FilterParams* p, int begin, int end) {
+    const int lane = threadIdx.x & 31;
+    for (int base = begin; base < end; base += 32) {
+        if (base + lane < end) {
+            const uint4 e = lds_v4(slots + (uint32_t)(base + lane) * 16u);
+            const unsigned int slot = atomicAdd(&p->cnt[e.z], 1u);
+            if (slot < p->cap) p->cand[(size_t)e.z * p->cap + slot] = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
         }
     }
-};
+}
 
 // The filter rounds fold the threshold into the MMA: one extra K=16 step multiplies a constant-ones slab with
 // (-thr_hi, -thr_lo), so the accumulator already holds score - thr and "is any of these 8 scores admissible"
@@ -87,16 +90,17 @@ __device__ __forceinline__ uint32_t and8(const uint32_t* v) {
     return (v[0] & v[1] & v[2]) & (v[3] & v[4] & v[5]) & (v[6] & v[7]);
 }
 
-// Compare W accumulator columns of one catalogue row against the thresholds of the W queries they belong to.
-template <int W, int MODE>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const float* thr_s, int c0, int q_base,
-                                               long long row, bool row_ok, const FilterParams& p, HitQueue& hq,
-                                               int lane, long long dense_pos) {
+// 32 accumulator columns of one catalogue row (already out of TMEM, the accumulator stage already released)
+// against the 32 queries they belong to.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* thr_s, int c0, int q_base,
+                                               uint32_t row, bool row_ok, const FilterParams& p, const HitCtx& h,
+                                               uint32_t dense_pos) {
     if (MODE == kModeDump) {
         if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-                int q = q_base + c0 + j;
+            for (int j = 0; j < 32; ++j) {
+                const int q = q_base + c0 + j;
                 if (q < p.B) p.dump[(size_t)row * p.dump_ld + q] = __uint_as_float(v[j]);
             }
         }
@@ -106,36 +110,33 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const flo
         // round 0 (open threshold): every score is a candidate, slot = position in the round, no atomics;
         // for a fixed query the 32 lanes write 32 consecutive keys (256 B, coalesced)
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
+        for (int j = 0; j < 32; ++j) {
             const int q = q_base + c0 + j;
             const float s = __uint_as_float(v[j]);
-            if (q < p.B) p.cand[(size_t)q * p.cap + dense_pos] = (row_ok && s == s) ? make_key(s, (uint32_t)row) : 0ull;
+            if (q < p.B) p.cand[(size_t)q * p.cap + dense_pos] = (row_ok && s == s) ? make_key(s, row) : 0ull;
         }
         return;
     }
-    uint32_t grp[W / 8];
+    uint32_t grp[4];
 #pragma unroll
-    for (int g = 0; g < W / 8; ++g) grp[g] = and8(&v[8 * g]);
-    uint32_t all = grp[0];
+    for (int g = 0; g < 4; ++g) grp[g] = and8(&v[8 * g]);
+    const uint32_t all = (grp[0] & grp[1]) & (grp[2] & grp[3]);
+    if ((int)all >= 0 && row_ok) {                 // this lane's row has a non-negative (score - thr): rare
 #pragma unroll
-    for (int g = 1; g < W / 8; ++g) all &= grp[g];
-    if (__any_sync(0xffffffffu, (int)all >= 0 && row_ok)) {     // warp-uniform from here on: no divergence
-#pragma unroll
-        for (int g = 0; g < W / 8; ++g) {
-            if (__any_sync(0xffffffffu, (int)grp[g] >= 0 && row_ok)) {
+        for (int g = 0; g < 4; ++g) {
+            if ((int)grp[g] >= 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float diff = __uint_as_float(v[8 * g + j]);            // score - thr (NaN stays NaN)
                     // the key carries score = diff + thr: one fp32 rounding (~3e-8), far inside the margin
-                    hq.push((diff >= 0.0f) & row_ok, diff + thr_s[c0 + 8 * g + j], (uint32_t)row,
-                            q_base + c0 + 8 * g + j, p, lane);
+                    if (diff >= 0.0f) push_hit(h.slots, h.count, &p, diff + thr_s[c0 + 8 * g + j], row, q_base + c0 + 8 * g + j);
                 }
             }
         }
     }
 }
 
-template <int MODE>
+template <int MODE, int KB>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -143,13 +144,12 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     // round trip through an integer) keeps the shared address space visible to the compiler: LDS/STS, not LD/ST.
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int nq = p.nq;
-    const int kb = p.kb;
+    const int nq = p.nq;                         // multiple of 32
     const int q_slab = nq * 128;                 // bytes of one K block of the query operand
-    const int stage_bytes = kb * kSlabBytes;
+    constexpr int stage_bytes = KB * kSlabBytes;
 
     uint8_t* q_smem = smem;
-    uint8_t* item_smem = q_smem + kb * q_slab;   // kb*q_slab is a multiple of 1024 (nq % 8 == 0)
+    uint8_t* item_smem = q_smem + KB * q_slab;   // KB*q_slab is a multiple of 1024 (nq % 8 == 0)
     uint8_t* ones_smem = item_smem + (size_t)p.stages * stage_bytes;   // [128 rows x K16] constant (1, 1, 0, ...)
     uint8_t* bias_smem = ones_smem + kBiasRowBytes * kTileItems;       // [nq rows x K16] (-thr_hi, -thr_lo, 0, ...)
     float* thr_s = reinterpret_cast<float*>(bias_smem + kBiasRowBytes * kMaxNQ);
@@ -160,11 +160,12 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     uint64_t* tfull_bar = bars + 2 * p.stages;            // [acc]      MMA -> epilogue
     uint64_t* tempty_bar = tfull_bar + p.acc_stages;      // [acc]      epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + p.acc_stages);
+    unsigned int* hitcnt_s = tmem_slot + 2;               // [kEpiWarps]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // epilogue warps that own at least one column chunk of this query-block width (narrow blocks: fewer warps)
-    const int parts_active = (nq + 31) / 32 < kColParts ? (nq + 31) / 32 : kColParts;
+    // epilogue warps that own at least one 32-column chunk of this query-block width (narrow blocks: fewer warps)
+    const int parts_active = nq / 32 < kColParts ? nq / 32 : kColParts;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
@@ -182,6 +183,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
+    if (threadIdx.x < kEpiWarps) hitcnt_s[threadIdx.x] = 0u;
     if (MODE == kModeFilter) {
         // constant A operand of the threshold MMA: K-major, no swizzle, 8-row core matrices of 128 B;
         // row r, columns 0..7 live at (r/8)*256 + (r%8)*16, columns 8..15 (all zero) 128 B further
@@ -201,15 +203,20 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     const uint32_t idesc = umma_idesc_bf16_f32(kTileItems, (uint32_t)nq);
     const uint64_t policy = p.stream_once ? l2_policy_evict_first() : l2_policy_evict_last();
 
-    // Pipeline positions persist across query blocks.
-    uint32_t stage = 0, phase = 0;        // smem ring (producer and MMA each keep a copy)
-    uint32_t acc = 0, acc_phase = 0;      // TMEM ring (MMA and epilogue each keep a copy)
+    // Tiles this CTA walks per query block, and the visiting order (32-bit: tile counts fit easily).
+    const int t_first = p.tile_begin + slot;
+    const int my_tiles = t_first < p.tile_end ? (p.tile_end - t_first + p.slots - 1) / p.slots : 0;
+    const uint32_t phys0 = (uint32_t)(((long long)t_first * p.tile_mul) % p.tile_mod);
+    const uint32_t tile_step = (uint32_t)p.tile_step, tile_mod = (uint32_t)p.tile_mod;
+    // Ring positions persist across query blocks; every role keeps private copies (so they can live in uniform
+    // registers where the role is warp-converged) re-derived from this count at the top of each block.
+    uint32_t tiles_done = 0;
 
     for (int qb = qb0; qb < p.nqb; qb += p.qb_step) {
         const int q_base = qb * nq;
         // ---- stage the query block: fp32 -> bf16 (RN), K-major, 128B swizzle ----
         {
-            const int chunks_per_row = kb * 8;   // 16-byte chunks (8 bf16) per query row
+            constexpr int chunks_per_row = KB * 8;   // 16-byte chunks (8 bf16) per query row
             for (int i = threadIdx.x; i < nq * chunks_per_row; i += kThreadsTc) {
                 const int r = i / chunks_per_row;
                 const int c = i - r * chunks_per_row;
@@ -264,15 +271,17 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         if (warp == 0) {
             // ===================== TMA producer =====================
             if (lane == 0) {
-                long long phys = ((long long)(p.tile_begin + slot) * p.tile_mul) % p.tile_mod;
-                for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+                uint32_t stage = tiles_done % (uint32_t)p.stages, phase = (tiles_done / (uint32_t)p.stages) & 1u;
+                uint32_t phys = phys0;
+                for (int it = 0; it < my_tiles; ++it) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                     uint8_t* dst = item_smem + (size_t)stage * stage_bytes;
-                    const int tile_row = (int)phys * kTileItems;
-                    phys += p.tile_step;                       // (slots * tile_mul) % tile_mod, from the host
-                    if (phys >= p.tile_mod) phys -= p.tile_mod;
-                    for (int k = 0; k < kb; ++k)
+                    const int tile_row = (int)(phys * (uint32_t)kTileItems);
+                    phys += tile_step;                         // (slots * tile_mul) % tile_mod, from the host
+                    if (phys >= tile_mod) phys -= tile_mod;
+#pragma unroll
+                    for (int k = 0; k < KB; ++k)
                         tma_load_2d(dst + k * kSlabBytes, &tmap, k * kKBlock, tile_row, &full_bar[stage], policy);
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -280,10 +289,9 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             __syncwarp();
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
-            // The whole warp walks the loop converged, so ring positions and descriptor halves stay in uniform
-            // registers; only the issue itself is predicated on the elected lane.  (Run by lane 0 alone, every
-            // operand took an ELECT + R2UR round trip: ~35 instructions per MMA, and the single issuing thread,
-            // not the tensor pipe, set the pace -- profiles/README.md, v4 -> v5.)
+            // The warp walks the loop converged (ring positions and descriptor halves stay in uniform registers);
+            // one elected lane issues a tile's MMAs and commits inside a single branch.  The K loop is unrolled at
+            // compile time: a tile is KB*4 (+1 threshold) tcgen05.mma whose descriptors differ by constants.
             const bool leader = elect_one();
             const uint32_t sw_hi = (uint32_t)(umma_desc_k_sw128(0) >> 32);
             const uint32_t ns_hi = (uint32_t)(umma_desc_k_noswizzle(0) >> 32);
@@ -291,92 +299,105 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             const uint32_t i_lo = (uint32_t)umma_desc_k_sw128(smem_u32(item_smem));
             const uint32_t ones_lo = (uint32_t)umma_desc_k_noswizzle(smem_u32(ones_smem));
             const uint32_t bias_lo = (uint32_t)umma_desc_k_noswizzle(smem_u32(bias_smem));
-            const uint32_t stage_step = (uint32_t)stage_bytes >> 4;     // descriptor address units are 16 bytes
+            constexpr uint32_t stage_step = (uint32_t)stage_bytes >> 4;     // descriptor address units are 16 bytes
             const uint32_t q_step = (uint32_t)q_slab >> 4;
-            for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+            uint32_t stage = tiles_done % (uint32_t)p.stages, phase = (tiles_done / (uint32_t)p.stages) & 1u;
+            uint32_t acc = tiles_done % (uint32_t)p.acc_stages, acc_phase = (tiles_done / (uint32_t)p.acc_stages) & 1u;
+            for (int it = 0; it < my_tiles; ++it) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)nq;
-                uint32_t a_lo = i_lo + stage * stage_step;
-                uint32_t b_lo = q_lo;
-                for (int k = 0; k < kb; ++k) {
-#pragma unroll
-                    for (int s = 0; s < kKBlock / 16; ++s)
-                        if (leader) umma_bf16_lohi(d_tmem, a_lo + 2 * s, sw_hi, b_lo + 2 * s, sw_hi, idesc, (k | s) ? 1u : 0u);
-                    a_lo += kSlabBytes >> 4;
-                    b_lo += q_step;
-                }
                 if (leader) {
+                    const uint32_t d_tmem = tmem_base + acc * (uint32_t)nq;
+                    const uint32_t a_lo = i_lo + stage * stage_step;
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) {
+#pragma unroll
+                        for (int s = 0; s < kKBlock / 16; ++s)
+                            umma_bf16_lohi(d_tmem, a_lo + k * (kSlabBytes >> 4) + 2 * s, sw_hi,
+                                           q_lo + k * q_step + 2 * s, sw_hi, idesc, (k | s) ? 1u : 0u);
+                    }
                     if (MODE == kModeFilter)        // accumulator -= thr (see epilogue_chunk)
                         umma_bf16_lohi(d_tmem, ones_lo, ns_hi, bias_lo, ns_hi, idesc, 1u);
                     umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
                     umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
                 }
+                __syncwarp();
                 if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
                 if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
-            __syncwarp();
         } else if (((warp - 2) >> 2) < parts_active) {
             // ===================== epilogue (up to 16 warps) =====================
+            // Per tile a warp owns 32 TMEM lanes (catalogue rows) x one or two 32-column chunks (queries).  It
+            // pulls them into registers, hands the accumulator stage straight back to the MMA warp, and only then
+            // looks at the values: the tensor pipe never waits for compare or hit handling.
             const int e = warp - 2;
             const uint32_t quad = (uint32_t)warp & 3u;   // TMEM lane quadrant this warp may read
-            const int part = e >> 2;                      // which of the interleaved 32-column chunks it takes
-            HitQueue hq;
-            hq.slots = hitq_s + e * kHitQueue;
-            hq.count = 0;
-            long long phys = ((long long)(p.tile_begin + slot) * p.tile_mul) % p.tile_mod;
-            for (int t = p.tile_begin + slot; t < p.tile_end; t += p.slots) {
+            const int part = e >> 2;                      // its chunks: columns 32*part and 32*part + 128
+            const bool two = 32 * part + 128 < nq;        // warp-uniform
+            HitCtx h;
+            h.slots = smem_u32(hitq_s + e * kHitQueue);
+            h.count = smem_u32(hitcnt_s + e);
+            volatile unsigned int* hit_count = hitcnt_s + e;
+            uint32_t acc = tiles_done % (uint32_t)p.acc_stages, acc_phase = (tiles_done / (uint32_t)p.acc_stages) & 1u;
+            uint32_t phys = phys0;
+            const uint32_t lane_row = quad * 32u + (uint32_t)lane;
+            const uint32_t n_items = (uint32_t)p.n_items;
+            const uint32_t tbase = tmem_base + ((quad * 32u) << 16) + 32u * (uint32_t)part;
+            const int c0 = 32 * part;
+            for (int it = 0; it < my_tiles; ++it) {
                 // deferred appends of the previous tile's hits: issue the slot-allocating atomics now ...
                 int pend = 0;
                 unsigned long long pkey = 0ull;
                 unsigned int pq = 0u, pslot = 0u;
-                if (MODE == kModeFilter && hq.count > 0) {
-                    if (hq.count > 32) {
-                        hq.flush_blocking(p, lane);
-                    } else {
-                        pend = hq.count;
+                if (MODE == kModeFilter) {
+                    __syncwarp();
+                    const unsigned int nh = *hit_count;
+                    if (nh) {
+                        const int m = nh < (unsigned int)kHitQueue ? (int)nh : kHitQueue;
+                        if (m > 32) hit_queue_flush(h.slots, &p, 32, m);
+                        pend = m < 32 ? m : 32;
                         if (lane < pend) {
-                            const uint4 en = hq.slots[lane];
+                            const uint4 en = lds_v4(h.slots + (uint32_t)lane * 16u);
                             pkey = (unsigned long long)en.x | ((unsigned long long)en.y << 32);
                             pq = en.z;
                             pslot = atomicAdd(&p.cnt[pq], 1u);
                         }
-                        hq.count = 0;
+                        __syncwarp();
+                        if (lane == 0) *hit_count = 0u;
                         __syncwarp();
                     }
                 }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after_sync();
-                const long long tile_pos = t - p.tile_begin;
-                const long long row = phys * kTileItems + quad * 32 + lane;
-                phys += p.tile_step;
-                if (phys >= p.tile_mod) phys -= p.tile_mod;
-                const bool row_ok = row < p.n_items;
-                const long long dense_pos = tile_pos * kTileItems + quad * 32 + lane;
-                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * (uint32_t)nq;
-                int c0 = 32 * part;
-                for (; c0 + 32 <= nq; c0 += 32 * kColParts) {
-                    uint32_t v[32];
-                    tmem_ld_x32(taddr + c0, v);
-                    tmem_ld_wait();
-                    epilogue_chunk<32, MODE>(v, thr_s, c0, q_base, row, row_ok, p, hq, lane, dense_pos);
-                }
-                if (c0 < nq && c0 + 16 == nq) {          // a trailing 16-column chunk belongs to exactly one part
-                    uint32_t v[16];
-                    tmem_ld_x16(taddr + c0, v);
-                    tmem_ld_wait();
-                    epilogue_chunk<16, MODE>(v, thr_s, c0, q_base, row, row_ok, p, hq, lane, dense_pos);
-                }
+                uint32_t v0[32], v1[32];
+                const uint32_t taddr = tbase + acc * (uint32_t)nq;
+                tmem_ld_x32(taddr, v0);
+                if (two) tmem_ld_x32(taddr + 128u, v1);
+                tmem_ld_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);        // values are in registers: release the stage
                 if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                const uint32_t row = phys * (uint32_t)kTileItems + lane_row;
+                phys += tile_step;
+                if (phys >= tile_mod) phys -= tile_mod;
+                const bool row_ok = row < n_items;
+                const uint32_t dense_pos = (uint32_t)(t_first - p.tile_begin + it * p.slots) * (uint32_t)kTileItems + lane_row;
+                epilogue_chunk<MODE>(v0, thr_s, c0, q_base, row, row_ok, p, h, dense_pos);
+                if (two) epilogue_chunk<MODE>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, h, dense_pos);
                 // ... and consume their results only now, a whole tile of work later
                 if (lane < pend && pslot < p.cap) p.cand[(size_t)pq * p.cap + pslot] = pkey;
             }
-            if (MODE == kModeFilter) hq.flush_blocking(p, lane);
+            if (MODE == kModeFilter) {
+                __syncwarp();
+                const unsigned int nh = *hit_count;
+                if (nh) hit_queue_flush(h.slots, &p, 0, nh < (unsigned int)kHitQueue ? (int)nh : kHitQueue);
+                __syncwarp();
+                if (lane == 0) *hit_count = 0u;
+            }
         }
+        tiles_done += (uint32_t)my_tiles;
         // All MMAs reading this query block have retired once every epilogue warp is here.
         __syncthreads();
     }
@@ -453,12 +474,47 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
     if (i < n) p[i] = v;
 }
 
+// One instantiation per (mode, K blocks); the opt-in shared-memory ceiling is a per-function, per-process setting.
+template <int MODE, int KB>
+cudaError_t launch_tc_one(int grid, size_t smem, const CUtensorMap& tmap, const FilterParams& p, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(score_filter_tc_kernel<MODE, KB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    score_filter_tc_kernel<MODE, KB><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_tc_mode(int kb, int grid, size_t smem, const CUtensorMap& tmap, const FilterParams& p,
+                           cudaStream_t stream) {
+    switch (kb) {
+        case 1: return launch_tc_one<MODE, 1>(grid, smem, tmap, p, stream);
+        case 2: return launch_tc_one<MODE, 2>(grid, smem, tmap, p, stream);
+        case 3: return launch_tc_one<MODE, 3>(grid, smem, tmap, p, stream);
+        case 4: return launch_tc_one<MODE, 4>(grid, smem, tmap, p, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_tc_variant(int mode, int kb, int grid, size_t smem, const CUtensorMap& tmap, const FilterParams& p,
+                              cudaStream_t stream) {
+    switch (mode) {
+        case kModeDump: return launch_tc_mode<kModeDump>(kb, grid, smem, tmap, p, stream);
+        case kModeDense: return launch_tc_mode<kModeDense>(kb, grid, smem, tmap, p, stream);
+        default: return launch_tc_mode<kModeFilter>(kb, grid, smem, tmap, p, stream);
+    }
+}
+
 }  // namespace
 
 size_t filter_tc_smem_bytes(int nq, int kb, int stages) {
     return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + kMaxNQ * sizeof(float) +
            (size_t)kBiasRowBytes * (kTileItems + kMaxNQ) + (size_t)kEpiWarps * kHitQueue * sizeof(uint4) +
-           (2 * stages + 8) * sizeof(uint64_t) + 16;
+           (2 * stages + 8) * sizeof(uint64_t) + 16 + kEpiWarps * sizeof(unsigned int);
 }
 
 int filter_tc_pick_stages(int nq, int kb) {
@@ -491,21 +547,8 @@ cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sm
     p.stream_once = (p.nqb == 1) ? 1 : 0;
     p.tile_step = ((long long)p.slots * p.tile_mul) % p.tile_mod;
     const size_t smem = filter_tc_smem_bytes(p.nq, p.kb, p.stages);
-    static bool attr_done = false;   // the opt-in shared-memory ceiling is a per-function, per-process setting
-    if (!attr_done) {
-        cudaError_t e;
-        if ((e = cudaFuncSetAttribute(score_filter_tc_kernel<kModeFilter>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(score_filter_tc_kernel<kModeDump>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(score_filter_tc_kernel<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) != cudaSuccess) return e;
-        attr_done = true;
-    }
-    if (p.dump)
-        score_filter_tc_kernel<kModeDump><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
-    else if (p.dense)
-        score_filter_tc_kernel<kModeDense><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
-    else
-        score_filter_tc_kernel<kModeFilter><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
-    return cudaGetLastError();
+    const int mode = p.dump ? kModeDump : (p.dense ? kModeDense : kModeFilter);
+    return launch_tc_variant(mode, p.kb, grid, smem, tmap, p, stream);
 }
 
 cudaError_t launch_filter_simt(const float* table, long long n_items, int d, const float* queries, int B,

@@ -15,7 +15,8 @@ table, shadow = hw.ops.blend_normalize(torch.randn((n, d), generator=g, device=d
 index = hw.ops.TopKIndex(table, shadow, max_norm=hw.ops.norm_stats(table)[4])
 
 
-def run(B, growth, late, steps):
+def run(B, growth, late, steps, first=1024):
+    os.environ["HWER_FIRST_ROWS"] = str(first)
     os.environ["HWER_GROWTH"] = str(growth)
     os.environ["HWER_LATE_ROWS"] = str(late)
     q = hw.ops.unit_length(torch.randn((B, d), generator=g, device=dev))
@@ -33,12 +34,21 @@ def run(B, growth, late, steps):
     ms = e0.elapsed_time(e1) / steps
     fms, fl, ol = index.profile_read()
     index.profile(False)
-    print("B=%5d growth=%2d late=%9d : %8.3f ms/step  %10.0f q/s  filter %7.3f ms  launches/step %.0f" %
-          (B, growth, late, ms, B / ms * 1e3, fms / steps, (fl + ol) / steps), flush=True)
+    print("B=%5d first=%5d growth=%2d late=%9d : %8.3f ms/step  %10.0f q/s  filter %7.3f ms  launches/step %.0f" %
+          (B, first, growth, late, ms, B / ms * 1e3, fms / steps, (fl + ol) / steps), flush=True)
 
 
-for B, steps in ((1, 50), (16, 50), (64, 50), (256, 30), (1024, 20), (4096, 10)):
-    for growth, late in ((16, 1 << 40), (16, 262144), (16, 1048576), (8, 262144), (8, 1048576), (4, 1 << 40), (32, 1 << 40), (32, 1048576)):
+CONFIGS = {
+    4096: [(1024, 8, 262144), (8192, 8, 262144), (8192, 4, 262144), (8192, 2, 1 << 40), (8192, 1, 0), (4096, 1, 0),
+           (16384, 1, 0), (8192, 4, 65536), (4096, 2, 1 << 40), (2048, 2, 1 << 40)],
+    1024: [(1024, 8, 262144), (8192, 8, 262144), (8192, 2, 1 << 40), (8192, 1, 0), (8192, 4, 65536)],
+    256: [(1024, 8, 262144), (8192, 8, 262144), (8192, 4, 1 << 40), (8192, 2, 1 << 40), (8192, 8, 1 << 40)],
+    64: [(1024, 8, 1048576), (8192, 8, 1048576), (8192, 8, 1 << 40), (8192, 16, 1 << 40), (8192, 32, 1 << 40), (16384, 32, 1 << 40)],
+    16: [(1024, 32, 1 << 40), (8192, 32, 1 << 40), (16384, 32, 1 << 40)],
+    1: [(1024, 32, 1 << 40), (8192, 32, 1 << 40), (16384, 32, 1 << 40)],
+}
+for B, steps in ((4096, 8), (1024, 15), (256, 20), (64, 40), (16, 40), (1, 40)):
+    for first, growth, late in CONFIGS[B]:
         if 3 * k * growth > 16384:
             continue
-        run(B, growth, late, steps)
+        run(B, growth, late, steps, first)
