@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: result exchange over NVLink peer stores fused into the final kernel, or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -256,7 +258,7 @@ def run_b200(a):
     table, shadow, blend_ms, blend_bytes = make_shard(hw, torch, a, begin, end, dev)
     viol, _, _, _, max_norm = hw.ops.norm_stats(table)
     assert viol == 0
-    shard = hw.sharded.ShardedTopK(table, begin, shadow=shadow, max_norm=max_norm)
+    shard = hw.sharded.ShardedTopK(table, begin, shadow=shadow, max_norm=max_norm, exchange=a.exchange)
     index = shard.index
     d_pad = shadow.shape[1]
 
@@ -265,6 +267,9 @@ def run_b200(a):
         return hw.ops.unit_length(torch.randn((B, a.dim), generator=g, device=dev))
 
     def step_device(q):
+        if world > 1 and a.exchange == "p2p":
+            idx, _, s64 = shard.topk_p2p_async(q, a.k, a.mode, want_f64=True)
+            return idx, s64
         idx, _, s64 = index.topk_async(q, min(a.k, index.n), a.mode, idx_offset=begin, want_f64=True)
         if world > 1:
             idx, s64 = hw.sharded.pad_local_result(idx, s64, a.k)
@@ -328,7 +333,7 @@ def run_b200(a):
     # (the clock sampler keeps running: both passes are the same work, and one pass can be shorter than a sample)
     pms, filt_ms, filt_l, other_l, _ = measure(a.batch, a.steps, 1, profile=True)
     clocks = sampler.stop() if sampler else None
-    launches_per_step = (filt_l + other_l) / a.steps + (1 if world > 1 else 0)
+    launches_per_step = (filt_l + other_l) / a.steps + (1 if world > 1 and a.exchange == "nccl" else 0)
     roof = roofline(a.batch, filt_ms / a.steps)
     roof["share_of_step"] = (filt_ms / a.steps) / (pms / a.steps)
 
@@ -381,7 +386,9 @@ def run_b200(a):
                                    "tables), exact top-%d by cosine, query batch %d, item-sharded over %d GPU(s)"
                                    % (a.alpha, a.k, a.batch, world),
                        "items": a.items, "dim": a.dim, "k": a.k, "batch": a.batch, "mode": a.mode,
-                       "parallelism": "item-shard x%d + all-gather/merge" % world if world > 1 else "single GPU",
+                       "parallelism": ("item-shard x%d + %s" % (world, "peer-store exchange fused into the final kernel + owner merge"
+                                                                      if a.exchange == "p2p" else "NCCL all-gather + merge"))
+                       if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (%.2f GB bf16 shadow per GPU streamed every step)"
                              % ((end - begin) * d_pad * 2 / 1e9)},
             "e2e": {"value": a.batch * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
@@ -395,6 +402,9 @@ def run_b200(a):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        if shard._px is not None:
+            shard._px.check()
+        shard.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -15,6 +15,9 @@ HWER_E_ARCH = -3
 HWER_E_K_TOO_LARGE = -4
 HWER_E_OVERFLOW = -5
 HWER_E_NOMEM = -6
+HWER_E_PEER = -7
+IPC_HANDLE_BYTES = 64
+PHASE_SEARCH, PHASE_MERGE, PHASE_COLLECT, PHASE_ALL = 1, 2, 4, 7
 MODE_EXACT = 0
 MODE_BF16 = 1
 
@@ -36,6 +39,16 @@ SIGNATURES = {
     "hwer_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
     "hwer_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "hwer_merge_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hwer_exchange_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "hwer_peer_alloc": (c_int, [c_int64, POINTER(c_void_p), c_void_p]),
+    "hwer_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "hwer_peer_close": (c_int, [c_void_p]),
+    "hwer_peer_free": (c_int, [c_void_p]),
+    "hwer_exchange_create": (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p), c_int32]),
+    "hwer_exchange_destroy": (c_int, [c_void_p]),
+    "hwer_topk_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_uint32, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_void_p]),
+    "hwer_exchange_error": (c_int, [c_void_p, c_void_p]),
     "hwer_pair_score": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hwer_eval_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),

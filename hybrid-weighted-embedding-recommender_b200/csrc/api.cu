@@ -267,9 +267,16 @@ int hwer_index_destroy(hwer_index_t* ix) {
     return HWER_OK;
 }
 
-int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
-              int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream_v) {
-    if (!ix || B < 0 || k <= 0 || (B > 0 && (!queries_dev || !out_idx_dev || !out_score_dev)))
+}  // extern "C"
+
+namespace {
+
+// The whole single-GPU pipeline (rounds of filter + select, then final).  With `peer` set, final_kernel stores
+// each query's result into the exchange buffer of the GPU that merges it instead of the local out arrays.
+int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
+              int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev,
+              const hwer::PeerDst* peer, void* stream_v) {
+    if (!ix || B < 0 || k <= 0 || (B > 0 && (!queries_dev || (!peer && (!out_idx_dev || !out_score_dev)))))
         return fail(HWER_E_INVALID, "hwer_topk: bad argument");
     if (mode != HWER_MODE_EXACT && mode != HWER_MODE_BF16) return fail(HWER_E_INVALID, "hwer_topk: unknown mode");
     if (mode == HWER_MODE_BF16 && !ix->use_tc)
@@ -310,7 +317,9 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         while (seen < T) {
             long long take = round == 0 ? sch.first_tiles : seen * (seen >= sch.late_tiles ? 1 : sch.growth);
             long long end = seen + take;
-            if (end > T || (T - end) * 4 < take) end = T;
+            if (end > T || (T - end) * 4 < take) end = T;          // absorb a short remainder into this round ...
+            if (round == 0 && end * hwer::kTileItems > (long long)sch.cap)   // ... unless the dense round would
+                end = seen + take < T ? seen + take : T;                      // outgrow the candidate lists
             const bool timed = prof_begin(ix, stream);
             if (ix->use_tc) {
                 hwer::FilterParams p;
@@ -340,11 +349,171 @@ int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
             seen = end;
             ++round;
         }
+        hwer::PeerDst pd;
+        if (peer) { pd = *peer; pd.q0 = q0; }
         HWER_CUDA(hwer::launch_final(ix->cand, ix->cnt, sch.cap, Bc, k, exact ? 1 : 0, ix->table, ix->d, Q, idx_offset,
-                                     (long long*)out_idx_dev + (size_t)q0 * k, out_score_dev + (size_t)q0 * k,
-                                     out_score64_dev ? out_score64_dev + (size_t)q0 * k : nullptr, ix->needed_dev,
-                                     stream));
+                                     peer ? nullptr : (long long*)out_idx_dev + (size_t)q0 * k,
+                                     peer ? nullptr : out_score_dev + (size_t)q0 * k,
+                                     (!peer && out_score64_dev) ? out_score64_dev + (size_t)q0 * k : nullptr,
+                                     ix->needed_dev, peer ? &pd : nullptr, stream));
     }
+    return HWER_OK;
+}
+
+}  // namespace
+
+struct hwer_exchange {
+    hwer::ExchangeView v;
+    unsigned int epoch = 0;
+    int device = 0;
+};
+
+namespace {
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct ExchangeLayout {
+    size_t flags, xs, xi, out_idx, out_score64, out_score, total;
+    int q_cap;
+};
+
+ExchangeLayout exchange_layout(int world, int b_cap, int k_cap) {
+    ExchangeLayout L;
+    L.q_cap = (b_cap + world - 1) / world;
+    const size_t x = (size_t)world * L.q_cap * k_cap * 8, o = (size_t)b_cap * k_cap;
+    size_t off = 0;
+    L.flags = off; off += 256;
+    L.xs = off; off += align256(x);
+    L.xi = off; off += align256(x);
+    L.out_idx = off; off += align256(o * 8);
+    L.out_score64 = off; off += align256(o * 8);
+    L.out_score = off; off += align256(o * 4);
+    L.total = off;
+    return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
+              int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream_v) {
+    return topk_impl(ix, queries_dev, B, k, mode, cap, idx_offset, out_idx_dev, out_score_dev, out_score64_dev, nullptr,
+                     stream_v);
+}
+
+int64_t hwer_exchange_bytes(int32_t world, int32_t b_cap, int32_t k_cap) {
+    if (world < 1 || world > hwer::kMaxPeers || b_cap < 1 || k_cap < 1) return -1;
+    return (int64_t)exchange_layout(world, b_cap, k_cap).total;
+}
+
+int hwer_peer_alloc(int64_t bytes, void** dev_ptr_out, unsigned char* handle_out) {
+    if (bytes <= 0 || !dev_ptr_out || !handle_out) return fail(HWER_E_INVALID, "hwer_peer_alloc: bad argument");
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HWER_E_NOMEM, "hwer_peer_alloc: cudaMalloc failed");
+    }
+    HWER_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    HWER_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == HWER_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail_cuda(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle_out, &h, sizeof h);
+    *dev_ptr_out = p;
+    return HWER_OK;
+}
+
+int hwer_peer_open(const unsigned char* handle, void** dev_ptr_out) {
+    if (!handle || !dev_ptr_out) return fail(HWER_E_INVALID, "hwer_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    HWER_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr_out = p;
+    return HWER_OK;
+}
+
+int hwer_peer_close(void* dev_ptr) {
+    if (dev_ptr) HWER_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return HWER_OK;
+}
+
+int hwer_peer_free(void* dev_ptr) {
+    if (dev_ptr) HWER_CUDA(cudaFree(dev_ptr));
+    return HWER_OK;
+}
+
+int hwer_exchange_create(hwer_exchange_t** out, int32_t world, int32_t rank, int32_t b_cap, int32_t k_cap,
+                         void* const* bases, int32_t device) {
+    if (!out || world < 1 || world > hwer::kMaxPeers || rank < 0 || rank >= world || b_cap < 1 || k_cap < 1 || !bases)
+        return fail(HWER_E_INVALID, "hwer_exchange_create: bad argument");
+    for (int r = 0; r < world; ++r)
+        if (!bases[r]) return fail(HWER_E_INVALID, "hwer_exchange_create: null peer buffer");
+    hwer_exchange* x = new hwer_exchange();
+    const ExchangeLayout L = exchange_layout(world, b_cap, k_cap);
+    memset(&x->v, 0, sizeof x->v);
+    x->v.world = world; x->v.rank = rank; x->v.q_cap = L.q_cap; x->v.k_cap = k_cap; x->v.b_cap = b_cap;
+    for (int r = 0; r < world; ++r) {
+        unsigned char* b = static_cast<unsigned char*>(bases[r]);
+        x->v.flags[r] = reinterpret_cast<unsigned int*>(b + L.flags);
+        x->v.xs[r] = reinterpret_cast<double*>(b + L.xs);
+        x->v.xi[r] = reinterpret_cast<long long*>(b + L.xi);
+        x->v.out_idx[r] = reinterpret_cast<long long*>(b + L.out_idx);
+        x->v.out_score64[r] = reinterpret_cast<double*>(b + L.out_score64);
+        x->v.out_score[r] = reinterpret_cast<float*>(b + L.out_score);
+    }
+    x->device = device;
+    *out = x;
+    return HWER_OK;
+}
+
+int hwer_exchange_destroy(hwer_exchange_t* x) {
+    delete x;
+    return HWER_OK;
+}
+
+int hwer_topk_sharded(hwer_index_t* ix, hwer_exchange_t* x, const float* queries_dev, int32_t B, int32_t k, int32_t mode,
+                      uint32_t cap, int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev,
+                      double* out_score64_dev, int32_t phases, void* stream_v) {
+    if (!ix || !x || B < 1 || k < 1 || !queries_dev || !out_idx_dev || !out_score_dev || !(phases & 7))
+        return fail(HWER_E_INVALID, "hwer_topk_sharded: bad argument");
+    if (B > x->v.b_cap || k > x->v.k_cap) return fail(HWER_E_INVALID, "hwer_topk_sharded: batch or k exceeds the exchange buffers");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    HWER_CUDA(cudaSetDevice(ix->device));
+    if (phases & HWER_PHASE_SEARCH) ++x->epoch;     // every rank calls in lockstep, so they agree on it
+    const unsigned int epoch = x->epoch;
+    x->v.q_per_owner = (B + x->v.world - 1) / x->v.world;
+    if (!(phases & HWER_PHASE_SEARCH)) {
+        if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));
+        if (phases & HWER_PHASE_COLLECT)
+            HWER_CUDA(hwer::launch_exchange_collect(x->v, B, k, epoch, (long long*)out_idx_dev, out_score_dev,
+                                                    out_score64_dev, stream));
+        return HWER_OK;
+    }
+    hwer::PeerDst pd;
+    memset(&pd, 0, sizeof pd);
+    pd.world = x->v.world; pd.rank = x->v.rank; pd.q_per_owner = x->v.q_per_owner; pd.q_cap = x->v.q_cap; pd.k_cap = x->v.k_cap;
+    for (int r = 0; r < x->v.world; ++r) { pd.xs[r] = x->v.xs[r]; pd.xi[r] = x->v.xi[r]; }
+    int rc = topk_impl(ix, queries_dev, B, k, mode, cap, idx_offset, nullptr, nullptr, nullptr, &pd, stream_v);
+    if (rc) return rc;
+    HWER_CUDA(hwer::launch_exchange_signal(x->v, 0, epoch, stream));
+    if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));
+    if (phases & HWER_PHASE_COLLECT)
+        HWER_CUDA(hwer::launch_exchange_collect(x->v, B, k, epoch, (long long*)out_idx_dev, out_score_dev,
+                                                out_score64_dev, stream));
+    ix->other_launches += 3;
+    return HWER_OK;
+}
+
+int hwer_exchange_error(hwer_exchange_t* x, void* stream_v) {
+    if (!x) return fail(HWER_E_INVALID, "hwer_exchange_error: null exchange");
+    HWER_CUDA(cudaSetDevice(x->device));
+    HWER_CUDA(cudaStreamSynchronize((cudaStream_t)stream_v));
+    unsigned int err = 0;
+    HWER_CUDA(cudaMemcpy(&err, x->v.flags[x->v.rank] + 17, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(HWER_E_PEER, "hwer_topk_sharded: timed out waiting for a peer GPU");
     return HWER_OK;
 }
 

@@ -65,10 +65,40 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
                                   cudaStream_t stream);
 
+// Where final_kernel stores a query's result when the catalogue is sharded over several GPUs: straight into the
+// exchange buffer of the GPU that owns (merges) that query, over NVLink peer stores (exchange.cu).
+constexpr int kMaxPeers = 8;
+struct PeerDst {
+    int world;                       // 0 = disabled (results go to the local out_* arrays)
+    int rank;
+    int q_per_owner;                 // Bq = ceil(B / world): owner(q) = q / Bq
+    int q_cap;                       // rows per source rank in every exchange buffer (>= Bq)
+    int k_cap;                       // columns per row (>= K)
+    long long q0;                    // global query index of this launch's first query (batch chunking)
+    double* xs[kMaxPeers];           // [world][q_cap][k_cap] fp64 scores, on each owner
+    long long* xi[kMaxPeers];        // [world][q_cap][k_cap] global rows
+};
+
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,
                          long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
-                         cudaStream_t stream);
+                         const PeerDst* peer, cudaStream_t stream);
+
+// Peer exchange (exchange.cu): publish "my scatter is complete" on every peer; owner-side wait + merge + delivery
+// of the merged rows to every rank; final wait + copy-out.
+struct ExchangeView {
+    int world, rank, q_per_owner, q_cap, k_cap, b_cap;
+    unsigned int* flags[kMaxPeers];      // per rank: [2][kMaxPeers] epochs + [16] scratch (counter, error)
+    double* xs[kMaxPeers];
+    long long* xi[kMaxPeers];
+    long long* out_idx[kMaxPeers];       // per rank: [b_cap, k_cap] merged rows (row stride k of the call)
+    float* out_score[kMaxPeers];
+    double* out_score64[kMaxPeers];
+};
+cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned int epoch, cudaStream_t stream);
+cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, cudaStream_t stream);
+cudaError_t launch_exchange_collect(const ExchangeView& v, int B, int K, unsigned int epoch, long long* out_idx,
+                                    float* out_score, double* out_score64, cudaStream_t stream);
 
 cudaError_t launch_merge(const double* scores, const long long* idx, int G, int B, int K, long long* out_idx,
                          float* out_score, double* out_score64, cudaStream_t stream);

@@ -113,7 +113,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
         for (int j = 0; j < 32; ++j) {
             const int q = q_base + c0 + j;
             const float s = __uint_as_float(v[j]);
-            if (q < p.B) p.cand[(size_t)q * p.cap + dense_pos] = (row_ok && s == s) ? make_key(s, row) : 0ull;
+            if (q < p.B && dense_pos < p.cap) p.cand[(size_t)q * p.cap + dense_pos] = (row_ok && s == s) ? make_key(s, row) : 0ull;
         }
         return;
     }

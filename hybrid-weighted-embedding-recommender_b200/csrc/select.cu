@@ -12,6 +12,8 @@
 //   merge          : G shards x K -> K with the same ordering rule (multi-GPU).
 //
 // One CTA per query; lists are sorted in shared memory with a bitonic network.
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -134,12 +136,145 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
     }
 }
 
+// The same selection with ONE WARP per query, for the filter rounds of large batches: their lists are short
+// (about k * (1 + 1.4 growth) keys), so a CTA per query spends its time in __syncthreads and leaves most of the
+// machine idle, while thousands of independent warps finish in one wave.  The list is re-read from L1/L2 in every
+// pass (a few KB per query) instead of being staged; the compaction is in place and order-preserving.
+constexpr int kSelWarps = 4;
+constexpr int kSelWarpKeys = 1024;          // keys staged per warp (8 KB); longer lists are re-read from L2
+
+__global__ void __launch_bounds__(kSelWarps * 32)
+select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap,
+                           int B, int K, const float* __restrict__ margin, float* __restrict__ thr,
+                           unsigned int* needed_cap) {
+    __shared__ unsigned long long keys_all[kSelWarps][kSelWarpKeys];
+    __shared__ unsigned int hist_all[kSelWarps][256];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int q = blockIdx.x * kSelWarps + w;
+    if (q >= B) return;
+    unsigned int* hist = hist_all[w];
+    unsigned int c_raw = cnt[q];
+    if (c_raw > cap) {
+        if (l == 0) atomicMax(needed_cap, c_raw);
+        c_raw = cap;
+    }
+    const int c = (int)c_raw;
+    unsigned long long* glist = cand + (size_t)q * cap;
+    // the list lives in shared memory when it fits (the normal case), else it is read through L2 every pass
+    const bool staged = c <= kSelWarpKeys;
+    volatile unsigned long long* list = staged ? keys_all[w] : glist;
+    unsigned int nvalid = 0;
+    for (int i = l; i < c; i += 32) {
+        const unsigned long long k = glist[i];
+        if (staged) keys_all[w][i] = k;
+        nvalid += (k != 0ull) ? 1u : 0u;
+    }
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
+    if ((int)nvalid >= K) {
+        unsigned int mask = 0u, prefix = 0u, remaining = (unsigned int)K;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) hist[8 * l + b] = 0u;
+            __syncwarp();
+            for (int i = l; i < c; i += 32) {
+                const unsigned long long k = list[i];
+                const unsigned int hi = (unsigned int)(k >> 32);
+                if (k != 0ull && (hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255u], 1u);
+            }
+            __syncwarp();
+            // lane l owns bins [8l, 8l+8); walk from the top bin down to the one holding the K-th key
+            unsigned int mine = 0u, h8[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { h8[b] = hist[8 * l + b]; mine += h8[b]; }
+            unsigned int above = mine;      // inclusive suffix sum over lanes >= l
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int x = __shfl_down_sync(0xffffffffu, above, o);
+                if (l + o < 32) above += x;
+            }
+            const unsigned int strictly_above = above - mine;
+            unsigned int found = 0u, new_rem = 0u;
+            if (strictly_above < remaining && remaining <= above) {
+                unsigned int acc = strictly_above;
+#pragma unroll
+                for (int b = 7; b >= 0; --b) {
+                    if (!found && acc + h8[b] >= remaining) {
+                        found = 0x100u | (unsigned int)(8 * l + b);
+                        new_rem = remaining - acc;
+                    }
+                    acc += h8[b];
+                }
+            }
+            const unsigned int owner = __ballot_sync(0xffffffffu, found != 0u);
+            const int src = __ffs(owner) - 1;                 // exactly one lane owns the K-th key's bin
+            found = __shfl_sync(0xffffffffu, found, src);
+            remaining = __shfl_sync(0xffffffffu, new_rem, src);
+            prefix |= (found & 255u) << shift;
+            mask |= 255u << shift;
+            __syncwarp();
+        }
+        const float sk = ordered_to_f32(prefix);
+        const float m = margin ? margin[q] : 0.0f;
+        t = sk - m;
+        if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
+    }
+    unsigned int kept = 0u;
+    for (int base = 0; base < c; base += 32) {
+        const int i = base + l;
+        const unsigned long long k = (i < c) ? list[i] : 0ull;
+        const bool keep = k != 0ull && key_score(k) >= t;
+        const unsigned int m = __ballot_sync(0xffffffffu, keep);
+        // order-preserving, and in place when unstaged: the write position never passes the batch being read
+        if (keep) glist[kept + __popc(m & ((1u << l) - 1u))] = k;
+        kept += __popc(m);
+        __syncwarp();
+    }
+    if (l == 0) {
+        cnt[q] = kept;
+        thr[q] = t;
+    }
+}
+
 // Exact fp64 dot of one fp32 table row with the fp32 query, one warp per
-// candidate, fixed summation order (deterministic).
+// candidate, fixed summation order (deterministic): lane l accumulates columns
+// l, l+32, ... in ascending order, then a butterfly over the lanes.
 __device__ __forceinline__ double exact_dot(const float* __restrict__ x, const float* __restrict__ qv, int d) {
     double s = 0.0;
     for (int c = lane_id(); c < d; c += 32) s = fma((double)x[c], (double)qv[c], s);
     return warp_sum(s);
+}
+
+// Same sums for widths that are a multiple of 128 with 16-byte aligned rows: each lane fetches its columns with
+// 128-bit loads, and two candidates are in flight per warp, because the row gathers (random 512-byte reads of a
+// multi-GB table) are latency-bound.  Lane l owns columns 4l..4l+3 of every 128-column block; the per-lane partial
+// sums differ from exact_dot's column assignment, so a table is always scored by ONE of the two variants
+// (fp32 x fp32 products are exact in fp64; the final rounding of the sum depends on the order).
+__device__ __forceinline__ void exact_dot2_v4(const float* __restrict__ xa, const float* __restrict__ xb,
+                                              const float4 (&qreg)[4], int nblk, double& sa, double& sb) {
+    sa = 0.0; sb = 0.0;
+    const int l = lane_id();
+    float4 a[4], c[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {           // all loads first: up to eight 128-bit gathers in flight per lane
+        if (b < nblk) {
+            a[b] = __ldg(reinterpret_cast<const float4*>(xa) + b * 32 + l);
+            c[b] = __ldg(reinterpret_cast<const float4*>(xb) + b * 32 + l);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (b < nblk) {
+            const float4 q = qreg[b];
+            sa = fma((double)a[b].x, (double)q.x, sa); sb = fma((double)c[b].x, (double)q.x, sb);
+            sa = fma((double)a[b].y, (double)q.y, sa); sb = fma((double)c[b].y, (double)q.y, sb);
+            sa = fma((double)a[b].z, (double)q.z, sa); sb = fma((double)c[b].z, (double)q.z, sb);
+            sa = fma((double)a[b].w, (double)q.w, sa); sb = fma((double)c[b].w, (double)q.w, sb);
+        }
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
 }
 
 template <bool EXACT>
@@ -147,7 +282,7 @@ __global__ void __launch_bounds__(kFinalThreads)
 final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned int cap,
              int K, const float* __restrict__ table, int d, const float* __restrict__ queries, long long idx_offset,
              long long* __restrict__ out_idx, float* __restrict__ out_score, double* __restrict__ out_score64,
-             unsigned int* needed_cap) {
+             unsigned int* needed_cap, const __grid_constant__ PeerDst peer) {
     extern __shared__ unsigned long long sm[];
     const int q = blockIdx.x;
     unsigned int c_raw = cnt[q];
@@ -163,13 +298,38 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
     if (EXACT) {
         const float* qv = queries + (size_t)q * d;
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        for (int i = warp; i < c; i += nwarps) {
-            const unsigned long long k = list[i];
-            const uint32_t row = key_row(k);
-            const double s = (k != 0ull) ? exact_dot(table + (size_t)row * d, qv, d) : 0.0;
-            if (lane_id() == 0) {
-                sk[i] = (k != 0ull && s == s) ? f64_to_ordered(s) : 0ull;
-                rw[i] = (k != 0ull && s == s) ? row : 0xffffffffu;
+        const bool vec = (d % 128 == 0) && d <= 512 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(qv)) & 15u) == 0;
+        if (vec) {
+            float4 qreg[4];
+            const int nblk = d / 128;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                qreg[b] = b < nblk ? __ldg(reinterpret_cast<const float4*>(qv) + b * 32 + lane_id()) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 2 * warp; i < c; i += 2 * nwarps) {
+                const unsigned long long ka = list[i];
+                const unsigned long long kb = (i + 1 < c) ? list[i + 1] : 0ull;
+                const uint32_t ra = key_row(ka), rb = key_row(kb);
+                double sa, sb;
+                exact_dot2_v4(table + (size_t)(ka != 0ull ? ra : 0u) * d, table + (size_t)(kb != 0ull ? rb : 0u) * d, qreg,
+                              nblk, sa, sb);
+                if (lane_id() == 0) {
+                    sk[i] = (ka != 0ull && sa == sa) ? f64_to_ordered(sa) : 0ull;
+                    rw[i] = (ka != 0ull && sa == sa) ? ra : 0xffffffffu;
+                    if (i + 1 < c) {
+                        sk[i + 1] = (kb != 0ull && sb == sb) ? f64_to_ordered(sb) : 0ull;
+                        rw[i + 1] = (kb != 0ull && sb == sb) ? rb : 0xffffffffu;
+                    }
+                }
+            }
+        } else {
+            for (int i = warp; i < c; i += nwarps) {
+                const unsigned long long k = list[i];
+                const uint32_t row = key_row(k);
+                const double s = (k != 0ull) ? exact_dot(table + (size_t)row * d, qv, d) : 0.0;
+                if (lane_id() == 0) {
+                    sk[i] = (k != 0ull && s == s) ? f64_to_ordered(s) : 0ull;
+                    rw[i] = (k != 0ull && s == s) ? row : 0xffffffffu;
+                }
             }
         }
         for (int i = c + threadIdx.x; i < P; i += blockDim.x) { sk[i] = 0ull; rw[i] = 0xffffffffu; }
@@ -187,6 +347,22 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
                       unsigned long long t = sk[a]; sk[a] = sk[b]; sk[b] = t;
                       uint32_t r = rw[a]; rw[a] = rw[b]; rw[b] = r;
                   });
+    if (peer.world > 0) {
+        // sharded catalogue: this query's local result goes straight to the GPU that merges it (NVLink peer
+        // stores, coalesced 8-byte words); that GPU learns about it from the flag published after this kernel
+        const long long qg = peer.q0 + q;
+        const int owner = (int)(qg / peer.q_per_owner);
+        const size_t o = ((size_t)peer.rank * peer.q_cap + (size_t)(qg - (long long)owner * peer.q_per_owner)) * peer.k_cap;
+        double* xs = peer.xs[owner] + o;
+        long long* xi = peer.xi[owner] + o;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            const bool ok = i < c && rw[i] != 0xffffffffu;
+            const double s = EXACT ? ordered_to_f64(sk[i]) : (double)ordered_to_f32((uint32_t)sk[i]);
+            xs[i] = ok ? s : -INFINITY;
+            xi[i] = ok ? (long long)rw[i] + idx_offset : -1;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         const size_t o = (size_t)q * K + i;
         if (i < c && rw[i] != 0xffffffffu) {
@@ -259,6 +435,11 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
                                   cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
+    if (fixed_count < 0 && B >= 128) {      // filter rounds of large batches: short lists, one warp per query
+        select_compact_warp_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(
+            cand, cnt, cap, B, K, margin, thr, needed_cap);
+        return cudaGetLastError();
+    }
     // stage only what can be there: a dense round holds fixed_count keys, a filter round at most cap
     const size_t n = fixed_count >= 0 ? (size_t)fixed_count : (size_t)cap;
     const size_t smem = (n < 1024 ? 1024 : n) * sizeof(unsigned long long);
@@ -271,20 +452,22 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,
                          long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
-                         cudaStream_t stream) {
+                         const PeerDst* peer, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = pow2_ge(cap) * (sizeof(unsigned long long) + sizeof(uint32_t));
+    PeerDst pd;
+    if (peer) pd = *peer; else memset(&pd, 0, sizeof pd);
     cudaError_t e;
     if (exact) {
         e = set_smem(final_kernel<true>, smem);
         if (e != cudaSuccess) return e;
         final_kernel<true><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset, out_idx,
-                                                            out_score, out_score64, needed_cap);
+                                                            out_score, out_score64, needed_cap, pd);
     } else {
         e = set_smem(final_kernel<false>, smem);
         if (e != cudaSuccess) return e;
         final_kernel<false><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
-                                                             out_idx, out_score, out_score64, needed_cap);
+                                                             out_idx, out_score, out_score64, needed_cap, pd);
     }
     return cudaGetLastError();
 }

@@ -148,6 +148,31 @@ class TopKIndex:
                                       _dev_ptr(score), _dev_ptr(s64), _stream(self.device)))
         return idx, score, s64
 
+    def topk_sharded_async(self, exchange, queries, k, mode="exact", idx_offset=0, cap=0, want_f64=False,
+                           phases=N.PHASE_ALL, out=None):
+        """hwer_topk_sharded: this shard's search, the peer-memory exchange and the owner-side merge, enqueued on
+        the current stream.  Collective over the exchange's ranks; returns the global [B, k] result."""
+        queries = _need(queries, torch.float32, "queries", 2)
+        if queries.shape[1] != self.d:
+            raise ValueError("query width %d != table width %d" % (queries.shape[1], self.d))
+        B, k = queries.shape[0], int(k)
+        if k > self.n:
+            raise ValueError("k=%d must be less than or equal to the number of rows %d of every shard" % (k, self.n))
+        if out is None:
+            idx = torch.empty((B, k), dtype=torch.int64, device=self.device)
+            score = torch.empty((B, k), dtype=torch.float32, device=self.device)
+            s64 = torch.empty((B, k), dtype=torch.float64, device=self.device) if want_f64 else None
+        else:
+            idx, score, s64 = out
+        m = N.MODE_EXACT if mode == "exact" else N.MODE_BF16 if mode == "bf16" else None
+        if m is None:
+            raise ValueError("mode must be 'exact' or 'bf16'")
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_topk_sharded(self._h, exchange._h, _dev_ptr(queries), B, k, m, int(cap),
+                                              int(idx_offset), _dev_ptr(idx), _dev_ptr(score), _dev_ptr(s64),
+                                              int(phases), _stream(self.device)))
+        return idx, score, s64
+
     def finish(self):
         need = c_uint32(0)
         with torch.cuda.device(self.device):

@@ -5,11 +5,13 @@ GPU g owns the contiguous catalogue rows [g*N/G, (g+1)*N/G); queries are replica
 local exact top-k (rows offset to global ids, fp64 scores), one all-gather exchanges the [B, k] results, and the
 merge kernel applies the same (score desc, row asc) rule -- so 1, 2, 4 and 8-GPU runs return identical results.
 """
+import ctypes
 from typing import Tuple
 
 import torch
 import torch.distributed as dist
 
+from . import _native as N
 from . import ops
 
 
@@ -40,20 +42,126 @@ def gather_shard_results(idx, s64, group=None):
     return allp[:, 0].contiguous().view(torch.float64), allp[:, 1].contiguous()
 
 
+class PeerExchange:
+    """The exchange buffers of hwer_topk_sharded (csrc/exchange.cu): one cudaMalloc'd buffer per rank, opened on
+    every other rank through CUDA IPC, so kernels store results straight into the peer that merges them.
+    torch.distributed only carries the 64-byte handles (host side, once)."""
+
+    def __init__(self, b_cap: int, k_cap: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.b_cap, self.k_cap = int(b_cap), int(k_cap)
+        self.device = torch.device(device)
+        lib = N.lib()
+        nbytes = lib.hwer_exchange_bytes(self.world, self.b_cap, self.k_cap)
+        if nbytes <= 0:
+            raise ValueError("bad exchange shape (world %d, batch %d, k %d)" % (self.world, b_cap, k_cap))
+        self._own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * N.IPC_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            N.check(lib.hwer_peer_alloc(nbytes, ctypes.byref(self._own), handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self._opened = []
+            bases = (ctypes.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    bases[r] = self._own
+                    continue
+                ptr = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * N.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                N.check(lib.hwer_peer_open(buf, ctypes.byref(ptr)))
+                self._opened.append(ptr)
+                bases[r] = ptr
+            self._h = ctypes.c_void_p()
+            N.check(lib.hwer_exchange_create(ctypes.byref(self._h), self.world, self.rank, self.b_cap, self.k_cap, bases,
+                                             self.device.index or 0))
+        dist.barrier(group=group)          # every rank has opened every buffer before anyone stores into one
+
+    def check(self):
+        """Synchronises the current stream; raises if a wait on a peer GPU timed out."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_exchange_error(self._h, ops._stream(self.device)))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if not h:
+            return
+        lib = N.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            lib.hwer_exchange_destroy(h)
+            for p in self._opened:
+                lib.hwer_peer_close(p)
+        try:
+            dist.barrier(group=self.group)  # nobody frees a buffer a peer still has open
+        except Exception:
+            pass
+        with torch.cuda.device(self.device):
+            lib.hwer_peer_free(self._own)
+
+    def __del__(self):
+        # freeing needs a collective; without an explicit close() the buffers live until the process exits
+        pass
+
+
 class ShardedTopK:
-    def __init__(self, local_table, row_offset: int, shadow=None, group=None, max_norm=None):
+    """One rank's share of an item-sharded catalogue.  `topk` returns the merged global result on every rank:
+    through the peer-memory exchange (`exchange="p2p"`, the default on a multi-GPU node) or through one NCCL
+    all-gather + local merge (`exchange="nccl"`)."""
+
+    def __init__(self, local_table, row_offset: int, shadow=None, group=None, max_norm=None, exchange="auto"):
         self.group = group
         self.row_offset = int(row_offset)
         self.index = ops.TopKIndex(local_table, shadow, max_norm=max_norm)
+        self.exchange = exchange
+        self._px = None
 
     def local_topk(self, queries, k, mode="exact"):
         kl = min(int(k), self.index.n)
         idx, _, s64 = self.index.topk(queries, kl, mode, idx_offset=self.row_offset, want_f64=True)
         return pad_local_result(idx, s64, int(k))
 
+    def _peer_exchange(self, B, k):
+        if self._px is None or self._px.b_cap < B or self._px.k_cap < k:
+            if self._px is not None:
+                self._px.close()
+            self._px = PeerExchange(max(B, 256), k, self.index.device, self.group)
+        return self._px
+
+    def topk_p2p_async(self, queries, k, mode="exact", cap=0, want_f64=False):
+        """Enqueues the fused search + peer exchange; results are valid after `finish_p2p()`."""
+        B, k = queries.shape[0], int(k)
+        px = self._peer_exchange(B, k)
+        return self.index.topk_sharded_async(px, queries, k, mode, idx_offset=self.row_offset, cap=cap,
+                                             want_f64=want_f64)
+
     def topk(self, queries, k, mode="exact"):
+        k = int(k)
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi and self.exchange in ("auto", "p2p") and self.index.n >= k and queries.is_cuda:
+            cap = 0
+            for _ in range(6):
+                idx, score, _ = self.topk_p2p_async(queries, k, mode, cap=cap)
+                rc, need = self.index.finish()
+                # an overflow on ANY rank re-runs the collective everywhere with the largest capacity asked for
+                t = torch.tensor([need if rc == N.HWER_E_OVERFLOW else 0], dtype=torch.int64, device=queries.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+                if rc not in (N.HWER_OK, N.HWER_E_OVERFLOW):
+                    N.check(rc)
+                cap = int(t.item())
+                if cap == 0:
+                    self._px.check()
+                    return idx, score
+            raise N.HwerError(N.HWER_E_OVERFLOW, "candidate lists kept overflowing")
         idx, s64 = self.local_topk(queries, k, mode)
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        if not multi:
             return idx, s64.float()
         gs, gi = gather_shard_results(idx, s64, self.group)
         return ops.merge_topk(gs, gi)
+
+    def close(self):
+        if self._px is not None:
+            self._px.close()
+            self._px = None

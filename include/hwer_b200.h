@@ -34,13 +34,16 @@ typedef enum hwer_status {
     HWER_E_ARCH = -3,        /* device is not sm_100 (B200)                                                 */
     HWER_E_K_TOO_LARGE = -4, /* k > rows of the index: sklearn's KDTree.query raises ValueError here        */
     HWER_E_OVERFLOW = -5,    /* candidate lists overflowed: re-run hwer_topk with cap >= *needed_cap        */
-    HWER_E_NOMEM = -6
+    HWER_E_NOMEM = -6,
+    HWER_E_PEER = -7         /* multi-GPU exchange: a peer GPU did not report in time                        */
 } hwer_status;
 
 #define HWER_MODE_EXACT 0 /* bf16 tensor-core filter with a proven margin + fp64 re-score from the fp32 table */
 #define HWER_MODE_BF16 1  /* bf16 tensor-core scores returned as they are                                    */
 
 typedef struct hwer_index hwer_index_t;
+typedef struct hwer_exchange hwer_exchange_t;
+#define HWER_IPC_HANDLE_BYTES 64
 
 const char* hwer_last_error(void);
 int hwer_version(void);
@@ -104,6 +107,35 @@ int hwer_debug_scores(hwer_index_t* index, const float* queries_dev, int32_t B, 
  * No reference counterpart (the reference is single-process); SURVEY.md section 8(e). */
 int hwer_merge_topk(const double* scores_dev, const int64_t* idx_dev, int32_t G, int32_t B, int32_t k,
                     int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream);
+
+/* ---- item-sharded search over the GPUs of one node, exchange over NVLink peer memory (no reference counterpart:
+ * the reference is single-process).  One process per GPU; GPU g indexes catalogue rows
+ * [g*N/G, (g+1)*N/G).  Every rank allocates one exchange buffer (hwer_exchange_bytes, hwer_peer_alloc), passes its
+ * 64-byte IPC handle to the others through any host channel (torch.distributed in the Python mirror), opens theirs
+ * (hwer_peer_open) and builds an exchange object over the `world` base pointers, its own included, in rank order.
+ *
+ * hwer_topk_sharded = hwer_topk on the local shard whose last kernel stores each query's result straight into
+ * the buffer of the GPU that owns the query (queries are split into `world` contiguous owner ranges), an owner-side
+ * merge that delivers the final rows to every rank, and a copy-out: out_* hold the same [B, k] result on every
+ * rank, bit-identical to a single-GPU hwer_topk over the whole table.  Collective: every rank must call it with
+ * the same B, k and mode, in the same order.  Each local shard needs at least k rows. */
+int64_t hwer_exchange_bytes(int32_t world, int32_t b_cap, int32_t k_cap);
+int hwer_peer_alloc(int64_t bytes, void** dev_ptr_out, unsigned char* handle_out /* [HWER_IPC_HANDLE_BYTES] */);
+int hwer_peer_open(const unsigned char* handle, void** dev_ptr_out);
+int hwer_peer_close(void* dev_ptr);
+int hwer_peer_free(void* dev_ptr);
+int hwer_exchange_create(hwer_exchange_t** out, int32_t world, int32_t rank, int32_t b_cap, int32_t k_cap,
+                         void* const* bases /* [world] device pointers */, int32_t device);
+int hwer_exchange_destroy(hwer_exchange_t* exchange);
+#define HWER_PHASE_SEARCH 1  /* local search; its last kernel stores into the owners' buffers; publish "scattered" */
+#define HWER_PHASE_MERGE 2   /* wait for every source, merge the owned queries, deliver to every rank, publish      */
+#define HWER_PHASE_COLLECT 4 /* wait for every owner, copy the [B, k] result into out_*                             */
+#define HWER_PHASE_ALL 7     /* the normal call; a host may also enqueue the phases one by one, in this order       */
+int hwer_topk_sharded(hwer_index_t* index, hwer_exchange_t* exchange, const float* queries_dev, int32_t B, int32_t k,
+                      int32_t mode, uint32_t cap, int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev,
+                      double* out_score64_dev, int32_t phases, void* stream);
+/* Synchronises `stream`; HWER_E_PEER if any wait on a peer timed out since the exchange was created. */
+int hwer_exchange_error(hwer_exchange_t* exchange, void* stream);
 
 /* out[p] = (dot(row src[p], row dst[p]) + 1) / 2; a row id outside [0, n) means "node not seen in training"
  * and scores with clip(row 0, 1e-6, 1e-5).

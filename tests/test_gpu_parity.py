@@ -172,6 +172,21 @@ def test_duplicates_follow_row_order_and_overflow_retries(hw):
     np.testing.assert_array_equal(idx2.cpu().numpy(), ref_idx)
 
 
+@pytest.mark.parametrize("n,B", [(10000, 9), (9000, 300), (5000, 600), (4500, 1000)])
+def test_catalogue_slightly_larger_than_dense_round(hw, n, B):
+    """A table a little longer than the dense first round (8192 / 4096 rows) must not push that round past the
+    candidate capacity: the raw entry point (no retry) has to succeed and be exact."""
+    from hwer_b200 import _native
+    t_np, t = unit_table(n, 128, 33)
+    q_np, q = unit_table(B, 128, 34)
+    index = hw.ops.TopKIndex(t)
+    idx, sc, s64 = index.topk_async(q, 10, want_f64=True)
+    rc, need = index.finish()
+    assert rc == _native.HWER_OK, (rc, need)
+    ref_idx, ref_sc = O.exact_topk(t_np, q_np, 10)
+    assert O.compare_topk(idx.cpu().numpy(), s64.cpu().numpy(), ref_idx, ref_sc, tie_eps=1e-6) == 0
+
+
 def test_sorted_clustered_catalogue(hw):
     """Rows sorted by cluster, queries aimed at the LAST cluster: the early rounds see other clusters only."""
     rs = np.random.RandomState(41)
@@ -378,6 +393,111 @@ def test_merge_and_shard_equivalence(hw):
         s, i = gs_n[:, r].reshape(-1), gi_n[:, r].reshape(-1)
         order = np.lexsort((i, -s))[:k]
         np.testing.assert_array_equal(idx[r].cpu().numpy(), i[order])
+
+
+class _Exchange:
+    """Bare exchange handle for topk_sharded_async (the product's PeerExchange also does the IPC rendezvous)."""
+    def __init__(self, h):
+        self._h = h
+
+
+@pytest.mark.parametrize("world,B,k", [(2, 50, 100), (3, 7, 10), (1, 33, 20)])
+def test_peer_exchange_protocol_on_one_gpu(hw, world, B, k):
+    """hwer_topk_sharded with `world` ranks living in ONE process: one exchange buffer, index (a row shard) and
+    stream per rank.  Exercises the real protocol -- final kernel storing into the owner's buffer, release/acquire
+    flags, owner merge delivering to every rank, collect -- and must reproduce the single-index answer bit for bit
+    on every rank, twice (buffer reuse across epochs)."""
+    import ctypes
+    from hwer_b200 import _native as N
+    lib = N.lib()
+    n, d = 30000, 128
+    t_np, t = unit_table(n, d, 91)
+    t_np[20000:20003] = t_np[5]                          # ties across shard boundaries
+    t = torch.from_numpy(t_np).cuda()
+    whole = hw.ops.TopKIndex(t)
+    nbytes = lib.hwer_exchange_bytes(world, 256, k)
+    assert nbytes > 0
+    bases = (ctypes.c_void_p * world)()
+    handle = (ctypes.c_ubyte * N.IPC_HANDLE_BYTES)()
+    for r in range(world):
+        ptr = ctypes.c_void_p()
+        N.check(lib.hwer_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+        bases[r] = ptr
+    ex, shards, streams = [], [], []
+    for r in range(world):
+        h = ctypes.c_void_p()
+        N.check(lib.hwer_exchange_create(ctypes.byref(h), world, r, 256, k, bases, 0))
+        ex.append(_Exchange(h))
+        b, e = hw.sharded.partition(n, world, r)
+        shards.append((hw.ops.TopKIndex(t[b:e].contiguous()), b))
+        shards[-1][0].topk(t[:B].contiguous(), k)        # sizes the workspace now (growing it synchronises the device)
+        streams.append(torch.cuda.Stream())
+    try:
+        for seed in (92, 93):
+            _, q = unit_table(B, d, seed)
+            ref_idx, ref_sc, ref_s64 = whole.topk(q, k, want_f64=True)
+            torch.cuda.synchronize()
+            outs = [(torch.empty((B, k), dtype=torch.int64, device="cuda"),
+                     torch.empty((B, k), dtype=torch.float32, device="cuda"),
+                     torch.empty((B, k), dtype=torch.float64, device="cuda")) for _ in range(world)]
+            torch.cuda.synchronize()
+            # one process plays every rank, so the phases are enqueued rank by rank, phase by phase: a rank's merge
+            # spins on the GPU until the other ranks' searches (already enqueued on their streams) have published
+            for phase in (N.PHASE_SEARCH, N.PHASE_MERGE, N.PHASE_COLLECT):
+                for r in range(world):
+                    with torch.cuda.stream(streams[r]):
+                        shards[r][0].topk_sharded_async(ex[r], q, k, idx_offset=shards[r][1], phases=phase, out=outs[r])
+            torch.cuda.synchronize()
+            for r in range(world):
+                N.check(lib.hwer_exchange_error(ex[r]._h, None))
+                assert torch.equal(outs[r][0], ref_idx), "rank %d rows differ" % r
+                assert torch.equal(outs[r][2], ref_s64) and torch.equal(outs[r][1], ref_sc)
+    finally:
+        torch.cuda.synchronize()
+        for r in range(world):
+            lib.hwer_exchange_destroy(ex[r]._h)
+            lib.hwer_peer_free(bases[r])
+
+
+def _p2p_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "oracle")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import hwer_b200 as hwm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n, d, B, k = 200000, 128, 300, 100
+    g = torch.Generator(device="cuda").manual_seed(7)
+    table = hwm.ops.unit_length(torch.randn((n, d), generator=g, device="cuda"))
+    q = hwm.ops.unit_length(torch.randn((B, d), generator=g, device="cuda"))
+    b, e = hwm.sharded.partition(n, world, rank)
+    res = {}
+    for ex in ("p2p", "nccl"):
+        sh = hwm.sharded.ShardedTopK(table[b:e].contiguous(), b, exchange=ex)
+        for _ in range(2):
+            idx, sc = sh.topk(q, k)
+        res[ex] = (idx.cpu(), sc.cpu())
+        sh.close()
+    whole_idx, whole_sc = hwm.ops.TopKIndex(table).topk(q, k)
+    assert torch.equal(res["p2p"][0], whole_idx.cpu()) and torch.equal(res["nccl"][0], whole_idx.cpu())
+    assert torch.equal(res["p2p"][1], res["nccl"][1])
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_peer_exchange_equals_nccl_and_single_gpu(tmp_path):
+    import os
+    import torch.multiprocessing as mp
+    port = 29600 + (os.getpid() % 1500)
+    mp.spawn(_p2p_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok0")) and os.path.exists(os.path.join(str(tmp_path), "ok1"))
 
 
 # ----------------------------------------------------------------------------- BASELINE.json full size (config C4)
