@@ -48,6 +48,12 @@ __device__ __forceinline__ void block_bitonic(int P, Before before, Swap swap) {
     }
 }
 
+// Histogram increment, one key per lane.  Plain shared-memory atomics: the hardware merges same-address updates
+// of a warp, and both ballot- and match-based aggregation measured slower (profiles/README.md, v7 notes).
+__device__ __forceinline__ void hist_add_aggregated(unsigned int* hist, bool take, unsigned int bin) {
+    if (take) atomicAdd(&hist[bin], 1u);
+}
+
 // K-th largest key prefix by radix select (4 passes x 8 bits over the order-preserving score image), then an
 // unordered compaction of everything at or above the new threshold.  O(c) work per query; a full sort of the
 // list is only needed once, in final_kernel, over the ~1.4 K survivors.
@@ -84,10 +90,11 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
             __syncthreads();
             const unsigned int prefix = sel_prefix;
-            for (int i = threadIdx.x; i < c; i += blockDim.x) {
-                const unsigned long long k = keys[i];
+            for (int base = 0; base < c; base += blockDim.x) {       // whole warps iterate together (match_any)
+                const int i = base + threadIdx.x;
+                const unsigned long long k = i < c ? keys[i] : 0ull;
                 const unsigned int hi = (unsigned int)(k >> 32);
-                if (k != 0ull && (hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255u], 1u);
+                hist_add_aggregated(hist, k != 0ull && (hi & mask) == prefix, (hi >> shift) & 255u);
             }
             __syncthreads();
             if (threadIdx.x < 32) {
@@ -125,9 +132,15 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
         t = sk - m;
         if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
     }
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
-        const unsigned long long k = keys[i];
-        if (k != 0ull && key_score(k) >= t) list[atomicAdd(&kept_s, 1u)] = k;
+    for (int base = 0; base < c; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned long long k = i < c ? keys[i] : 0ull;
+        const bool keep = k != 0ull && key_score(k) >= t;
+        const unsigned int m = __ballot_sync(0xffffffffu, keep);       // one slot-allocating atomic per warp
+        unsigned int slot = 0u;
+        if (lane_id() == 0 && m) slot = atomicAdd(&kept_s, (unsigned int)__popc(m));
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (keep) list[slot + __popc(m & ((1u << lane_id()) - 1u))] = k;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -178,10 +191,11 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
 #pragma unroll
             for (int b = 0; b < 8; ++b) hist[8 * l + b] = 0u;
             __syncwarp();
-            for (int i = l; i < c; i += 32) {
-                const unsigned long long k = list[i];
+            for (int base = 0; base < c; base += 32) {
+                const int i = base + l;
+                const unsigned long long k = i < c ? list[i] : 0ull;
                 const unsigned int hi = (unsigned int)(k >> 32);
-                if (k != 0ull && (hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255u], 1u);
+                hist_add_aggregated(hist, k != 0ull && (hi & mask) == prefix, (hi >> shift) & 255u);
             }
             __syncwarp();
             // lane l owns bins [8l, 8l+8); walk from the top bin down to the one holding the K-th key
@@ -255,30 +269,22 @@ __device__ __forceinline__ void exact_dot2_v4(const float* __restrict__ xa, cons
                                               const float4 (&qreg)[4], int nblk, double& sa, double& sb) {
     sa = 0.0; sb = 0.0;
     const int l = lane_id();
-    float4 a[4], c[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {           // all loads first: up to eight 128-bit gathers in flight per lane
-        if (b < nblk) {
-            a[b] = __ldg(reinterpret_cast<const float4*>(xa) + b * 32 + l);
-            c[b] = __ldg(reinterpret_cast<const float4*>(xb) + b * 32 + l);
-        }
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        if (b < nblk) {
-            const float4 q = qreg[b];
-            sa = fma((double)a[b].x, (double)q.x, sa); sb = fma((double)c[b].x, (double)q.x, sb);
-            sa = fma((double)a[b].y, (double)q.y, sa); sb = fma((double)c[b].y, (double)q.y, sb);
-            sa = fma((double)a[b].z, (double)q.z, sa); sb = fma((double)c[b].z, (double)q.z, sb);
-            sa = fma((double)a[b].w, (double)q.w, sa); sb = fma((double)c[b].w, (double)q.w, sb);
-        }
+#pragma unroll 1
+    for (int b = 0; b < nblk; ++b) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xa) + b * 32 + l);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(xb) + b * 32 + l);
+        const float4 q = b == 0 ? qreg[0] : (b == 1 ? qreg[1] : (b == 2 ? qreg[2] : qreg[3]));
+        sa = fma((double)a.x, (double)q.x, sa); sb = fma((double)c.x, (double)q.x, sb);
+        sa = fma((double)a.y, (double)q.y, sa); sb = fma((double)c.y, (double)q.y, sb);
+        sa = fma((double)a.z, (double)q.z, sa); sb = fma((double)c.z, (double)q.z, sb);
+        sa = fma((double)a.w, (double)q.w, sa); sb = fma((double)c.w, (double)q.w, sb);
     }
     sa = warp_sum(sa);
     sb = warp_sum(sb);
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kFinalThreads)
+__global__ void __launch_bounds__(kFinalThreads, 2)      // two CTAs (32 warps) per SM: the row gathers are latency-bound
 final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned int cap,
              int K, const float* __restrict__ table, int d, const float* __restrict__ queries, long long idx_offset,
              long long* __restrict__ out_idx, float* __restrict__ out_score, double* __restrict__ out_score64,
