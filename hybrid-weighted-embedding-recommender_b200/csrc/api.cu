@@ -598,6 +598,30 @@ int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t*
     return HWER_OK;
 }
 
+int64_t hwer_ncf_param_count(int32_t F, int32_t depth) {
+    if (F <= 0 || depth < 1 || depth > 16) return -1;
+    return hwer::ncf_param_count(F, depth);
+}
+
+int hwer_ncf_score(const float* h_dev, int64_t n_rows, int32_t F, int32_t depth, const float* params_dev,
+                   const int64_t* src_dev, const int64_t* dst_dev, int64_t P, float* out_dev, void* stream_v) {
+    if (!h_dev || n_rows <= 0 || F <= 0 || F % 4 || depth < 1 || depth > 16 || !params_dev || P < 0 ||
+        (P > 0 && (!src_dev || !dst_dev || !out_dev)))
+        return fail(HWER_E_INVALID, "hwer_ncf_score: bad argument (F must be a positive multiple of 4)");
+    if (P == 0) return HWER_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const long long chunk = P < 32768 ? P : 32768;
+    float *ws0 = nullptr, *ws1 = nullptr;
+    HWER_CUDA(cudaMallocAsync(&ws0, sizeof(float) * (size_t)chunk * 4 * F, stream));
+    HWER_CUDA(cudaMallocAsync(&ws1, sizeof(float) * (size_t)chunk * 2 * F, stream));
+    cudaError_t e = hwer::launch_ncf_score(h_dev, n_rows, F, depth, params_dev, (const long long*)src_dev,
+                                           (const long long*)dst_dev, P, out_dev, ws0, ws1, chunk, stream);
+    cudaFreeAsync(ws0, stream);
+    cudaFreeAsync(ws1, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "hwer_ncf_score");
+    return HWER_OK;
+}
+
 int hwer_eval_metrics(const int64_t* topk_dev, int32_t U, int32_t kret, const int64_t* train_ptr_dev,
                       const int64_t* train_idx_dev, const int64_t* val_ptr_dev, const int64_t* val_idx_dev,
                       const float* val_rel_dev, const int32_t* cutoffs_dev, int32_t n_cut, int64_t n_items,

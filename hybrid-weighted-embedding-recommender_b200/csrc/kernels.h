@@ -120,4 +120,12 @@ cudaError_t launch_eval_reduce(const double* per_user, int U, int M, const long 
                                const unsigned int* seen_bitmap, long long n_items, int n_cut, double* out,
                                cudaStream_t stream);
 
+// NCF re-rank (ncf.cu): params = [W1 (out x in, row-major), b1, ..., W_depth, b_depth, w_out (F), b_out (1)].
+int ncf_layer_in(int F, int depth, int layer);
+int ncf_layer_out(int F, int depth, int layer);
+long long ncf_param_count(int F, int depth);
+cudaError_t launch_ncf_score(const float* h, long long n_rows, int F, int depth, const float* params,
+                             const long long* src, const long long* dst, long long P, float* out, float* ws0,
+                             float* ws1, long long chunk, cudaStream_t stream);
+
 }  // namespace hwer

@@ -226,6 +226,30 @@ def merge_topk(scores64, idx, want_f64=False):
     return (o_idx, o_sc, o_s64) if want_f64 else (o_idx, o_sc)
 
 
+def ncf_param_count(F, depth):
+    return int(N.lib().hwer_ncf_param_count(int(F), int(depth)))
+
+
+def ncf_score(h, params, src_rows, dst_rows, depth):
+    """sigmoid(w_out . MLP([h[src] || h[dst]]) + b_out) per pair (hwer/ncf.py:7-27).  `h` is the reference's
+    prediction_artifacts["h"] ([N + 1, F], row 0 = padding node); rows are node rows + 1, anything out of range
+    reads row 0.  `params`: flat fp32 [W1, b1, ..., W_depth, b_depth, w_out, b_out] (torch Linear layout)."""
+    h = _need(h, torch.float32, "h", 2)
+    params = _need(params, torch.float32, "params", 1)
+    src_rows = _need(src_rows, torch.int64, "src_rows", 1)
+    dst_rows = _need(dst_rows, torch.int64, "dst_rows", 1)
+    F = h.shape[1]
+    if params.shape[0] != ncf_param_count(F, depth):
+        raise ValueError("params has %d floats, an NCF of width %d and depth %d needs %d"
+                         % (params.shape[0], F, depth, ncf_param_count(F, depth)))
+    P = src_rows.shape[0]
+    out = torch.empty(P, dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        N.check(N.lib().hwer_ncf_score(_dev_ptr(h), h.shape[0], F, int(depth), _dev_ptr(params), _dev_ptr(src_rows),
+                                       _dev_ptr(dst_rows), P, _dev_ptr(out), _stream(h.device)))
+    return out
+
+
 def pair_score(table, src_rows, dst_rows):
     """(dot + 1) / 2 of row pairs; row -1 = node unseen in training (hwer/recommendation_base.py:135-151)."""
     table = _need(table, torch.float32, "table", 2)

@@ -10,6 +10,8 @@ onwards:
   GcnNCF.fit tail                     hwer/gcn_ncf.py:439-445
   GcnNCF.predict (cosine branch)      hwer/gcn_ncf.py:330-334
   GcnNCF.find_closest_neighbours      hwer/gcn_ncf.py:363-383             score = (2 - euclidean distance) / 2
+  GcnNCF.predict (NCF branch)         hwer/gcn_ncf.py:336-361             sigmoid(MLP([h_src || h_dst])), hwer/ncf.py:7-27
+  GcnNCF.find_closest_neighbours      hwer/gcn_ncf.py:384-386             NCF re-rank of the k retrieved nodes
 """
 import operator
 from typing import Dict, List, Set, Tuple
@@ -46,8 +48,36 @@ class GcnNCF(RecommendationBase):
         assert n_dims % 2 == 0
         self.embedding_mapper = embedding_mapper
         self.alpha = alpha            # weight of the content table in the blend; 0.0 = the reference's behaviour
-        self.ncf_enabled = False      # the NCF re-rank (gcn_ncf.py:336-361,384-386) is not built yet
+        self.ncf_enabled = False      # set by set_ncf(): the reference sets it when ncf_epochs > 0 (gcn_ncf.py:437)
+        self.prediction_artifacts = dict()
         self.shadow = None
+
+    def set_ncf(self, h, params, depth):
+        """Installs a trained NCF re-ranker (the reference's prediction_artifacts {"model", "h"}, gcn_ncf.py:320-322).
+        h: [N + 1, n_dims] NCF input vectors, row 0 = the padding node; params: the flat fp32 parameter vector
+        [W1, b1, ..., W_depth, b_depth, w_out, b_out] in torch Linear layout (e.g. concatenated from
+        `model.W` of hwer/ncf.py); depth: ncf_layers."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        h = _as_device_table(h, dev)
+        if isinstance(params, np.ndarray):
+            params = torch.from_numpy(np.ascontiguousarray(params, dtype=np.float32))
+        params = params.to(dev, torch.float32).contiguous()
+        if params.shape[0] != ops.ncf_param_count(h.shape[1], depth):
+            raise ValueError("NCF parameter vector does not match width %d, depth %d" % (h.shape[1], depth))
+        self.prediction_artifacts = {"h": h, "params": params, "depth": int(depth)}
+        self.ncf_enabled = True
+        return self
+
+    def predict_rows(self, src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
+        if not self.ncf_enabled:
+            return super().predict_rows(src_rows, dst_rows)
+        pa = self.prediction_artifacts
+        # gcn_ncf.py:341-342: node row + 1, unknown node -> 0 (the padding row)
+        return ops.ncf_score(pa["h"], pa["params"], (src_rows + 1).clamp(min=0), (dst_rows + 1).clamp(min=0), pa["depth"])
+
+    def predict(self, node_pairs):
+        res = super().predict(node_pairs)
+        return list(res) if self.ncf_enabled else res      # the reference returns a list here (gcn_ncf.py:360-361)
 
     def prepare_for_knn(self, content_vectors, collaborative_vectors, alpha=None):
         """unit(alpha * unit(content) + (1 - alpha) * unit(collaborative)) on the device; numpy in -> numpy out."""
@@ -91,10 +121,21 @@ class GcnNCF(RecommendationBase):
         embedding = self._query_embedding(anchor, positive, negative)
         node_dist_list = self.knn.query(embedding, node_type, k=k)
         nodes, dist = zip(*node_dist_list)
+        if self.ncf_enabled:                                                          # gcn_ncf.py:384-386
+            scores = self.predict([(anchor, node) for node in nodes])
+            return list(sorted(zip(nodes, scores), key=operator.itemgetter(1), reverse=True))
         dist = (-1 * np.array(dist) + 2) / 2                                          # gcn_ncf.py:381
         return list(sorted(zip(nodes, dist), key=operator.itemgetter(1), reverse=True))
 
     def _batch_scores(self, anchor_rows, rows, dots):
+        if self.ncf_enabled:
+            # one NCF pass over all B * k (anchor, candidate) pairs, then the per-anchor descending sort of :386
+            B, k = rows.shape
+            s = self.predict_rows(anchor_rows[:, None].expand(B, k).reshape(-1).contiguous(),
+                                  rows.clamp(min=-1).reshape(-1).contiguous()).reshape(B, k)
+            s = torch.where(rows >= 0, s, torch.full_like(s, float("-inf")))
+            s, order = torch.sort(s, dim=1, descending=True, stable=True)
+            return torch.gather(rows, 1, order), s
         # (2 - ||q - x||) / 2 with q the unit anchor row: distance from the fp64 difference like KDTree64
         B, k = rows.shape
         q = ops.unit_length(self.device_vectors.index_select(0, anchor_rows)).double()

@@ -144,6 +144,18 @@ int hwer_exchange_error(hwer_exchange_t* exchange, void* stream);
 int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t* src_dev, const int64_t* dst_dev,
                     int64_t P, float* out_dev, void* stream);
 
+/* NCF re-rank: out[p] = sigmoid(w_out . MLP([h[src[p]] || h[dst[p]]]) + b_out), fp32.
+ * Replaces: NCF.forward, hwer/ncf.py:7-27, as driven by GcnNCF.predict, hwer/gcn_ncf.py:336-361, and by the NCF
+ *           branch of GcnNCF.find_closest_neighbours, hwer/gcn_ncf.py:384-386.
+ * h_dev [n_rows, F] is the reference's prediction_artifacts["h"] (row 0 = padding node; callers pass node row + 1,
+ * rows outside [0, n_rows) read row 0 like the reference's "unknown node -> 0").  The MLP has `depth` Linear +
+ * LeakyReLU(0.01) layers of widths F*iw -> F*ow with iw = 4 if layer == 2 else 2, ow = 1 if layer == depth else
+ * (4 if layer == 1 else 2) (ncf.py:12-16).  params_dev = [W1 (out x in row-major, torch layout), b1, ...,
+ * W_depth, b_depth, w_out (F), b_out (1)], hwer_ncf_param_count(F, depth) floats.  F must be a multiple of 4. */
+int64_t hwer_ncf_param_count(int32_t F, int32_t depth);
+int hwer_ncf_score(const float* h_dev, int64_t n_rows, int32_t F, int32_t depth, const float* params_dev,
+                   const int64_t* src_dev, const int64_t* dst_dev, int64_t P, float* out_dev, void* stream);
+
 /* Ranking metrics for U users in one pass.
  * Replaces: the per-user loops of validation.extraction_efficiency, hwer/validation.py:133-174, with
  *           utils.reciprocal_rank / ndcg / binary_ndcg / recall, hwer/utils.py:71-121.

@@ -95,6 +95,34 @@ def recall(y_true, y_pred):
 
 
 # --------------------------------------------------------------------------- exact brute-force k-NN
+def ncf_layer_dims(F, depth):
+    """(in, out) of every Linear of the reference NCF, hwer/ncf.py:12-16, then the (F, 1) output layer :19."""
+    dims = []
+    for layer_idx in range(1, depth + 1):
+        iw = 4 if layer_idx == 2 else 2
+        ow = 1 if layer_idx == depth else (4 if layer_idx == 1 else 2)
+        dims.append((F * iw, F * ow))
+    return dims + [(F, 1)]
+
+
+def ncf_forward(h, src, dst, params, depth):
+    """hwer/ncf.py:24-27 at inference (GaussianNoise is the identity in eval mode, hwer/gcn.py:32-38): fp32
+    Linear + LeakyReLU(0.01) stack over [h[src] || h[dst]], Linear(F, 1), sigmoid.  `params` = flat
+    [W1 (out x in), b1, ..., w_out, b_out]."""
+    h = np.asarray(h, dtype=np.float32)
+    x = np.concatenate([h[src], h[dst]], axis=1)
+    dims = ncf_layer_dims(h.shape[1], depth)
+    off = 0
+    for li, (i, o) in enumerate(dims):
+        w = params[off:off + i * o].reshape(o, i).astype(np.float32); off += i * o
+        b = params[off:off + o].astype(np.float32); off += o
+        x = x @ w.T + b
+        if li < len(dims) - 1:
+            x = np.where(x > 0, x, np.float32(0.01) * x)
+    assert off == len(params)
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).reshape(-1)
+
+
 def exact_topk(table, queries, k, block=4096):
     """Exact top-k by dot product: float64 scores over the stored rows, ordered (-score, row).
     This is what KDTree64.query computes on unit rows (Euclidean order == dot order),

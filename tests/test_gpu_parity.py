@@ -500,6 +500,67 @@ def test_two_gpu_peer_exchange_equals_nccl_and_single_gpu(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "ok0")) and os.path.exists(os.path.join(str(tmp_path), "ok1"))
 
 
+# ----------------------------------------------------------------------------- NCF re-rank
+@pytest.fixture(scope="module")
+def golden_ncf():
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "reference_ncf.npz"))
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+def test_ncf_score_matches_reference(hw, golden_ncf, depth):
+    """hwer_ncf_score against the reference NCF module's own outputs (tests/golden/reference_ncf.npz): 1e-5."""
+    g = golden_ncf
+    out = hw.ops.ncf_score(torch.from_numpy(g["h"]).cuda(), torch.from_numpy(g["params_d%d" % depth]).cuda(),
+                           torch.from_numpy(g["src"]).cuda(), torch.from_numpy(g["dst"]).cuda(), depth)
+    np.testing.assert_allclose(out.cpu().numpy(), g["forward_d%d" % depth], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("F,depth,P", [(128, 3, 70001), (64, 2, 333), (36, 4, 1000), (256, 3, 4097)])
+def test_ncf_score_matches_oracle_at_serving_widths(hw, F, depth, P):
+    rs = np.random.RandomState(61)
+    n = 5000
+    h = (rs.standard_normal((n + 1, F)) * 0.3).astype(np.float32)
+    params = np.concatenate([np.concatenate([(rs.standard_normal((o, i)) / np.sqrt(i)).reshape(-1),
+                                             rs.standard_normal(o) * 0.1]) for i, o in O.ncf_layer_dims(F, depth)])
+    params = params.astype(np.float32)
+    src = rs.randint(-1, n + 3, P).astype(np.int64)             # includes out-of-range rows (-> padding row 0)
+    dst = rs.randint(0, n + 1, P).astype(np.int64)
+    out = hw.ops.ncf_score(torch.from_numpy(h).cuda(), torch.from_numpy(params).cuda(), torch.from_numpy(src).cuda(),
+                           torch.from_numpy(dst).cuda(), depth).cpu().numpy()
+    src_c = np.where((src < 0) | (src > n), 0, src)
+    ref = O.ncf_forward(h, src_c, dst, params, depth)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-5)
+
+
+def test_gcn_ncf_rerank_matches_reference(hw, golden_ncf):
+    """GcnNCF with the NCF branch enabled: predict (incl. unknown nodes) and find_closest_neighbours re-ranked by
+    the NCF, against the reference's own outputs (gcn_ncf.py:336-361, 363-387)."""
+    g = golden_ncf
+    n_users, n_items, F, k = [int(x) for x in g["shape"]]
+    users = [hw.Node("user", i) for i in range(n_users)]
+    items = [hw.Node("item", i) for i in range(n_items)]
+    edges = [hw.Edge(users[i % n_users], items[i % n_items], 1.0) for i in range(100)]
+    model = hw.GcnNCF(None, {"user", "item"}, n_dims=F)
+    model.fit(users + items, edges, None, collaborative_vectors=g["table"])
+    model.set_ncf(g["h"], g["params_d3"], 3)
+    inv = model.nodes_to_idx.inverse
+    pairs = []
+    for a, b in zip(g["predict_src"], g["predict_dst"]):
+        pairs.append((inv[int(a)] if a >= 0 else hw.Node("user", "ghost"), inv[int(b)] if b >= 0 else hw.Node("item", "ghost")))
+    pred = model.predict(pairs)
+    assert isinstance(pred, list)
+    np.testing.assert_allclose(np.asarray(pred, dtype=np.float64), g["predict"], rtol=0, atol=1e-5)
+    for j, u in enumerate(g["anchors"]):
+        res = model.find_closest_neighbours("item", users[int(u)], k=k)
+        assert [int(n.node_external_id) for n, s in res] == list(g["fcn_idx"][j])
+        np.testing.assert_allclose([s for n, s in res], g["fcn_score"][j], rtol=0, atol=1e-5)
+    rows, sc = model.find_closest_neighbours_batch("item", [users[int(u)] for u in g["anchors"]], k=k)
+    np.testing.assert_array_equal(rows.cpu().numpy() - n_users, g["fcn_idx"])
+    np.testing.assert_allclose(sc.cpu().numpy(), g["fcn_score"], rtol=0, atol=1e-5)
+
+
 # ----------------------------------------------------------------------------- BASELINE.json full size (config C4)
 def test_full_size_properties_10m(hw):
     """10M x 128, top-100 (the headline workload): properties that do not need a CPU pass over the table."""

@@ -1,10 +1,12 @@
 """CPU: the oracle (oracle/hwer_oracle.py) against outputs of the REFERENCE ITSELF (tests/golden/*.npz, made by
 oracle/make_golden.py from /root/reference).  This is what pins the oracle."""
+import os
+
 import numpy as np
 import pytest
 
 import hwer_oracle as O
-from conftest import synthetic_case, synthetic_edges
+from conftest import GOLDEN, synthetic_case, synthetic_edges
 
 
 @pytest.fixture(scope="module")
@@ -151,3 +153,24 @@ def test_compare_topk_tie_rule():
     assert O.compare_topk(np.array([[5, 9, 3, 1]]), ref_sc, ref_idx, ref_sc) == 0     # swap inside a tie group
     assert O.compare_topk(np.array([[3, 5, 9, 1]]), ref_sc, ref_idx, ref_sc) == 1     # real reordering
     assert O.compare_topk(np.array([[5, 3, 9, 7]]), ref_sc, ref_idx, ref_sc) == 0     # tie straddling the cut
+
+
+# ----------------------------------------------------------------------------- NCF re-rank
+@pytest.fixture(scope="module")
+def golden_ncf():
+    return np.load(os.path.join(GOLDEN, "reference_ncf.npz"))
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+def test_ncf_forward_matches_reference(golden_ncf, depth):
+    """The oracle's restatement of hwer/ncf.py against the reference module's own outputs (its own initialisation)."""
+    g = golden_ncf
+    got = O.ncf_forward(g["h"], g["src"], g["dst"], g["params_d%d" % depth], depth)
+    np.testing.assert_allclose(got, g["forward_d%d" % depth], rtol=0, atol=2e-6)
+
+
+def test_ncf_predict_indexing_matches_reference(golden_ncf):
+    """GcnNCF.predict's row convention (gcn_ncf.py:341-342): node row + 1, unknown node -> padding row 0."""
+    g = golden_ncf
+    got = O.ncf_forward(g["h"], g["predict_src"] + 1, g["predict_dst"] + 1, g["params_d3"], 3)
+    np.testing.assert_allclose(got, g["predict"], rtol=0, atol=2e-6)
