@@ -50,6 +50,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_int32, c_void_p]),
     "hwer_exchange_error": (c_int, [c_void_p, c_void_p]),
     "hwer_pair_score": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "hwer_compose_queries": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int32, c_void_p, c_void_p]),
     "hwer_ncf_param_count": (c_int64, [c_int32, c_int32]),
     "hwer_ncf_score": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                c_void_p]),

@@ -598,6 +598,19 @@ int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t*
     return HWER_OK;
 }
 
+int hwer_compose_queries(const float* table_dev, int64_t n, int32_t d, const int64_t* anchor_rows_dev,
+                         const int64_t* pos_ptr_dev, const int64_t* pos_rows_dev, const int64_t* neg_ptr_dev,
+                         const int64_t* neg_rows_dev, int32_t B, float* out_dev, void* stream) {
+    if (!table_dev || n <= 0 || d <= 0 || d > 1024 || B < 0 || (B > 0 && (!anchor_rows_dev || !out_dev)) ||
+        (pos_ptr_dev && !pos_rows_dev) || (neg_ptr_dev && !neg_rows_dev))
+        return fail(HWER_E_INVALID, "hwer_compose_queries: bad argument (d <= 1024)");
+    HWER_CUDA(hwer::launch_compose_queries(table_dev, n, d, (const long long*)anchor_rows_dev,
+                                           (const long long*)pos_ptr_dev, (const long long*)pos_rows_dev,
+                                           (const long long*)neg_ptr_dev, (const long long*)neg_rows_dev, B, out_dev,
+                                           (cudaStream_t)stream));
+    return HWER_OK;
+}
+
 int64_t hwer_ncf_param_count(int32_t F, int32_t depth) {
     if (F <= 0 || depth < 1 || depth > 16) return -1;
     return hwer::ncf_param_count(F, depth);

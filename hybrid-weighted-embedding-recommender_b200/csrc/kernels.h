@@ -112,6 +112,10 @@ cudaError_t launch_norm_stats(const float* v, long long n, int d, float eps, dou
 cudaError_t launch_pair_score(const float* table, long long n, int d, const long long* src, const long long* dst,
                               long long P, float* out, cudaStream_t stream);
 
+cudaError_t launch_compose_queries(const float* table, long long n, int d, const long long* anchor,
+                                   const long long* pos_ptr, const long long* pos_rows, const long long* neg_ptr,
+                                   const long long* neg_rows, int B, float* out, cudaStream_t stream);
+
 cudaError_t launch_eval(const long long* topk, int U, int Kret, const long long* train_ptr,
                         const long long* train_idx, const long long* val_ptr, const long long* val_idx,
                         const float* val_rel, const int* cutoffs, int n_cut, long long n_items,

@@ -39,6 +39,73 @@ pair_score_kernel(const float* __restrict__ table, long long n, int d, const lon
 }
 
 // ---------------------------------------------------------------------------
+// Query composition: hwer/recommendation_base.py:164-170 (same in gcn_ncf.py:369-376)
+//   embedding = average([unit(mean(anchor)), unit(mean(positive)), -unit(mean(negative))])
+// over the parts that are present; NOT re-normalised.  One warp per query; a row id outside [0, n) is a node that
+// was never trained on and contributes clip(row 0, 1e-6, 1e-5) (get_embeddings, :146-151).  d <= 1024.
+// ---------------------------------------------------------------------------
+constexpr int kComposeMaxPerLane = 32;
+
+__device__ __forceinline__ void mean_unit_accumulate(const float* __restrict__ table, long long n, int d,
+                                                     const long long* __restrict__ rows, long long b, long long e,
+                                                     float sign, float (&acc)[kComposeMaxPerLane]) {
+    const int lane = lane_id();
+    float m[kComposeMaxPerLane];
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) m[j] = 0.f;
+    for (long long i = b; i < e; ++i) {
+        const long long r = rows[i];
+        const bool unk = r < 0 || r >= n;
+        const float* x = table + (size_t)(unk ? 0 : r) * d;
+#pragma unroll
+        for (int j = 0; j < kComposeMaxPerLane; ++j) {
+            const int c = lane + 32 * j;
+            if (c < d) {
+                float v = x[c];
+                if (unk) v = unknown_clip(v);
+                m[j] += v;
+            }
+        }
+    }
+    const float inv_cnt = 1.0f / (float)(e - b);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) { m[j] *= inv_cnt; ss = fmaf(m[j], m[j], ss); }
+    ss = warp_sum(ss);
+    const float inv_norm = sign / sqrtf(ss);
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) acc[j] = fmaf(m[j], inv_norm, acc[j]);
+}
+
+__global__ void __launch_bounds__(256)
+compose_queries_kernel(const float* __restrict__ table, long long n, int d, const long long* __restrict__ anchor,
+                       const long long* __restrict__ pos_ptr, const long long* __restrict__ pos_rows,
+                       const long long* __restrict__ neg_ptr, const long long* __restrict__ neg_rows, int B,
+                       float* __restrict__ out) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= B) return;
+    float acc[kComposeMaxPerLane];
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) acc[j] = 0.f;
+    int parts = 1;
+    mean_unit_accumulate(table, n, d, anchor, q, q + 1, 1.0f, acc);
+    if (pos_ptr && pos_ptr[q + 1] > pos_ptr[q]) {
+        mean_unit_accumulate(table, n, d, pos_rows, pos_ptr[q], pos_ptr[q + 1], 1.0f, acc);
+        ++parts;
+    }
+    if (neg_ptr && neg_ptr[q + 1] > neg_ptr[q]) {
+        mean_unit_accumulate(table, n, d, neg_rows, neg_ptr[q], neg_ptr[q + 1], -1.0f, acc);
+        ++parts;
+    }
+    const float inv = 1.0f / (float)parts;
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) {
+        const int c = lane_id() + 32 * j;
+        if (c < d) out[(size_t)q * d + c] = acc[j] * inv;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Evaluation: one warp per user.
 // per_user row layout (M = 3 * n_cut + 1 doubles):
 //   [3*c + 0] recall@cut[c]   [3*c + 1] ndcg@cut[c] (graded)   [3*c + 2] binary ndcg@cut[c]
@@ -184,6 +251,16 @@ cudaError_t launch_pair_score(const float* table, long long n, int d, const long
     long long blocks = (P + 7) / 8;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     pair_score_kernel<<<(int)blocks, 256, 0, stream>>>(table, n, d, src, dst, P, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compose_queries(const float* table, long long n, int d, const long long* anchor,
+                                   const long long* pos_ptr, const long long* pos_rows, const long long* neg_ptr,
+                                   const long long* neg_rows, int B, float* out, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    if (d > 32 * kComposeMaxPerLane) return cudaErrorInvalidValue;
+    compose_queries_kernel<<<(B + 7) / 8, 256, 0, stream>>>(table, n, d, anchor, pos_ptr, pos_rows, neg_ptr, neg_rows, B,
+                                                            out);
     return cudaGetLastError();
 }
 

@@ -226,6 +226,28 @@ def merge_topk(scores64, idx, want_f64=False):
     return (o_idx, o_sc, o_s64) if want_f64 else (o_idx, o_sc)
 
 
+def compose_queries(table, anchor_rows, pos=None, neg=None):
+    """Query vectors of a batch of find_closest_neighbours calls (hwer/recommendation_base.py:164-170):
+    average of unit(anchor row), unit(mean(positive rows)), -unit(mean(negative rows)) over the parts present.
+    pos / neg: None or (ptr [B+1] int64, rows int64) CSR lists; row -1 = node never trained on."""
+    table = _need(table, torch.float32, "table", 2)
+    anchor_rows = _need(anchor_rows, torch.int64, "anchor_rows", 1)
+    B = anchor_rows.shape[0]
+    out = torch.empty((B, table.shape[1]), dtype=torch.float32, device=table.device)
+    pp = pr = np_ = nr = None
+    if pos is not None:
+        pp, pr = _need(pos[0], torch.int64, "pos ptr", 1), _need(pos[1], torch.int64, "pos rows", 1)
+        assert pp.shape[0] == B + 1
+    if neg is not None:
+        np_, nr = _need(neg[0], torch.int64, "neg ptr", 1), _need(neg[1], torch.int64, "neg rows", 1)
+        assert np_.shape[0] == B + 1
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_compose_queries(_dev_ptr(table), table.shape[0], table.shape[1], _dev_ptr(anchor_rows),
+                                             _dev_ptr(pp), _dev_ptr(pr), _dev_ptr(np_), _dev_ptr(nr), B, _dev_ptr(out),
+                                             _stream(table.device)))
+    return out
+
+
 def ncf_param_count(F, depth):
     return int(N.lib().hwer_ncf_param_count(int(F), int(depth)))
 

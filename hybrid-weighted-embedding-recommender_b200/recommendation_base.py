@@ -247,13 +247,24 @@ class RecommendationBase(metaclass=abc.ABCMeta):
             emb[mask] = emb[mask].clamp(1e-6, 1e-5)
         return ops.unit_length(emb.mean(dim=0, keepdim=True))[0]
 
+    def _csr_rows(self, lists):
+        """Per-anchor node lists -> (ptr [B+1], rows) device CSR for ops.compose_queries."""
+        ptr, rows = [0], []
+        for nodes in lists:
+            rows.extend(self.nodes_to_idx[n] if n in self.nodes_to_idx else -1 for n in (nodes or []))
+            ptr.append(len(rows))
+        dev = self.device_vectors.device
+        return (torch.tensor(ptr, dtype=torch.int64, device=dev), torch.tensor(rows, dtype=torch.int64, device=dev))
+
+    def _query_embeddings(self, anchors, positive=None, negative=None) -> torch.Tensor:
+        """[B, d] query vectors of :164-170 for a batch of anchors; positive / negative: None or one node list per
+        anchor (empty or None entries = that part is absent for the anchor)."""
+        pos = self._csr_rows(positive) if positive is not None and any(positive) else None
+        neg = self._csr_rows(negative) if negative is not None and any(negative) else None
+        return ops.compose_queries(self.device_vectors, self._rows_of(anchors), pos, neg)
+
     def _query_embedding(self, anchor, positive=None, negative=None) -> torch.Tensor:
-        embedding_list = [self._average_embedding(self._rows_of([anchor]))]          # :164
-        if positive is not None and len(positive) > 0:
-            embedding_list.append(self._average_embedding(self._rows_of(positive)))  # :165-166
-        if negative is not None and len(negative) > 0:
-            embedding_list.append(-1 * self._average_embedding(self._rows_of(negative)))   # :167-168
-        return torch.stack(embedding_list).mean(dim=0)                                # :170 (not re-normalised)
+        return self._query_embeddings([anchor], [positive] if positive else None, [negative] if negative else None)[0]
 
     # ------------------------------------------------------------------ retrieval
     def _check_query(self, node_type, anchor):
@@ -294,18 +305,19 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         s, order = torch.sort(s, dim=1, descending=True, stable=True)
         return torch.gather(rows, 1, order), s
 
-    def find_closest_neighbours_batch(self, node_type: str, anchors: List[Node], k=200
+    def find_closest_neighbours_batch(self, node_type: str, anchors: List[Node], k=200,
+                                      positive: List[List[Node]] = None, negative: List[List[Node]] = None
                                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """One search for all anchors (the loop of validation.model_get_topk_knn, hwer/validation.py:30-35).
         Returns device tensors (global rows [B, k], scores [B, k]) in the same order and score convention as
-        find_closest_neighbours(node_type, anchor, k=k) called per anchor."""
+        find_closest_neighbours(node_type, anchor, positive[i], negative[i], k) called per anchor."""
         assert self.fit_done
         assert node_type in self.node_types and node_type in self.knn.knn
         for a in anchors:
             if a not in self.nodes_to_idx:
                 raise NodeNotFoundException("Node = %s, was not provided in training" % a)
         anchor_rows = self._rows_of(anchors)
-        queries = ops.unit_length(self.device_vectors.index_select(0, anchor_rows))
+        queries = self._query_embeddings(anchors, positive, negative)
         rows, dots = self.knn.query_batch(queries, node_type, k=k)
         return self._batch_scores(anchor_rows, rows, dots)
 

@@ -144,6 +144,17 @@ int hwer_exchange_error(hwer_exchange_t* exchange, void* stream);
 int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t* src_dev, const int64_t* dst_dev,
                     int64_t P, float* out_dev, void* stream);
 
+/* Query vectors of a batch of find_closest_neighbours calls:
+ *   out[q] = average of { unit(row anchor[q]), unit(mean(rows pos[q])), -unit(mean(rows neg[q])) } over the parts
+ *   present, not re-normalised.
+ * Replaces: RecommendationBase.find_closest_neighbours' embedding composition, hwer/recommendation_base.py:164-170
+ *           (get_average_embeddings :153-155, get_embeddings :146-151), identical in hwer/gcn_ncf.py:369-376.
+ * pos/neg are CSR lists over the queries (ptr [B+1], rows); either ptr may be NULL.  Row ids outside [0, n) are
+ * nodes never trained on: clip(row 0, 1e-6, 1e-5).  d <= 1024. */
+int hwer_compose_queries(const float* table_dev, int64_t n, int32_t d, const int64_t* anchor_rows_dev,
+                         const int64_t* pos_ptr_dev, const int64_t* pos_rows_dev, const int64_t* neg_ptr_dev,
+                         const int64_t* neg_rows_dev, int32_t B, float* out_dev, void* stream);
+
 /* NCF re-rank: out[p] = sigmoid(w_out . MLP([h[src[p]] || h[dst[p]]]) + b_out), fp32.
  * Replaces: NCF.forward, hwer/ncf.py:7-27, as driven by GcnNCF.predict, hwer/gcn_ncf.py:336-361, and by the NCF
  *           branch of GcnNCF.find_closest_neighbours, hwer/gcn_ncf.py:384-386.

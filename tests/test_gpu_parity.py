@@ -500,6 +500,68 @@ def test_two_gpu_peer_exchange_equals_nccl_and_single_gpu(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "ok0")) and os.path.exists(os.path.join(str(tmp_path), "ok1"))
 
 
+# ----------------------------------------------------------------------------- query composition
+@pytest.mark.parametrize("d", [64, 100, 256])
+def test_compose_queries_matches_oracle(hw, d):
+    """hwer_compose_queries against the oracle's restatement of recommendation_base.py:164-170 (itself pinned to
+    the reference's positive/negative outputs in tests/golden/reference_c1.npz)."""
+    rs = np.random.RandomState(71)
+    n, B = 500, 40
+    t_np, t = unit_table(n, d, 72)
+    nodes = [O.Node("item", i) for i in range(n)]
+    rec = O.OracleRecommender({"item"}, n_dims=d)
+    rec.add_nodes(nodes)
+    rec.build_knn(t_np)
+    ghost = O.Node("item", "ghost")
+    anchors, pos, neg = [], [], []
+    for b in range(B):
+        anchors.append(int(rs.randint(n)))
+        pos.append([int(x) for x in rs.randint(0, n, rs.randint(0, 4))] if b % 3 else [])
+        neg.append([int(x) for x in rs.randint(0, n, rs.randint(0, 3))] if b % 2 else [])
+    pos[5] = pos[5] + [-1]                              # a node that was never trained on
+    want = np.stack([rec.query_embedding(nodes[a], [nodes[i] if i >= 0 else ghost for i in p] or None,
+                                         [nodes[i] for i in ng] or None) for a, p, ng in zip(anchors, pos, neg)])
+
+    def csr(lists):
+        ptr = np.cumsum([0] + [len(x) for x in lists]).astype(np.int64)
+        rows = np.array([i for x in lists for i in x], dtype=np.int64)
+        return torch.from_numpy(ptr).cuda(), torch.from_numpy(rows).cuda()
+
+    got = hw.ops.compose_queries(t, torch.tensor(anchors, dtype=torch.int64, device="cuda"), csr(pos), csr(neg))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-6)
+    only_anchor = hw.ops.compose_queries(t, torch.tensor(anchors, dtype=torch.int64, device="cuda"))
+    np.testing.assert_allclose(only_anchor.cpu().numpy(), t_np[anchors], rtol=0, atol=2e-6)
+
+
+def test_batch_posneg_equals_per_anchor(c1_model, hw):
+    model, users, items, g = c1_model["base"], c1_model["users"], c1_model["items"], c1_model["g"]
+    anchors = [users[int(u)] for u in g["user_anchors"][:16]]
+    n_items = len(items)
+    pos = [[items[(int(u) * 3 + j) % n_items] for j in range(3)] for u in g["user_anchors"][:16]]
+    neg = [[items[(int(u) * 5 + j + 1) % n_items] for j in range(2)] for u in g["user_anchors"][:16]]
+    k = int(g["shape"][3])
+    rows, sc = model.find_closest_neighbours_batch("item", anchors, k=k, positive=pos, negative=neg)
+    got = rows.cpu().numpy() - len(users)
+    np.testing.assert_array_equal(got, g["posneg_idx"])                 # the reference's own outputs
+    np.testing.assert_allclose(sc.cpu().numpy(), g["posneg_score"], rtol=0, atol=1e-5)
+
+
+def test_table_file_to_device_and_serve(hw, tmp_path):
+    """save_table -> load_table(device='cuda', one shard's rows) -> index: same answers as the in-memory table."""
+    import os
+    t_np, t = unit_table(20000, 128, 75)
+    _, q = unit_table(9, 128, 76)
+    p = os.path.join(str(tmp_path), "items.hwer")
+    hw.table_io.save_table(p, t, node_types={"item": (0, 20000)})
+    full, hdr = hw.table_io.load_table(p, device="cuda", chunk_rows=3000)
+    assert torch.equal(full, t) and hdr["unit_norm"]
+    want = hw.ops.TopKIndex(t).topk(q, 10)
+    got = hw.ops.TopKIndex(full).topk(q, 10)
+    assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])
+    half, _ = hw.table_io.load_table(p, device="cuda", rows=(10000, 20000), chunk_rows=4096)
+    assert torch.equal(half, t[10000:])
+
+
 # ----------------------------------------------------------------------------- NCF re-rank (SURVEY 8f-3)
 @pytest.fixture(scope="module")
 def golden_ncf():
