@@ -57,6 +57,20 @@ def peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, basis="of fallback")
 
 
+def ncu_traffic(batch):
+    """DRAM bytes (read + write) of the filter kernel per step, from the newest committed ncu capture
+    (profiles/r*_traffic.json, scripts/gpu_traffic.sh); None if this batch size was not captured."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        b = json.load(open(files[-1]))["batches"].get(str(batch))
+        return b["dram_read_bytes_per_step"] + b["dram_write_bytes_per_step"], os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -314,17 +328,21 @@ def run_b200(a):
 
     def roofline(B, filt_ms_per_step):
         rows = end - begin
+        byt = rows * d_pad * 2.0 + B * a.dim * 4.0 + B * a.k * 8.0
+        # measured DRAM traffic of the same kernel (ncu, per step): only valid for the captured shape (N = 1, C4)
+        traffic, src = ncu_traffic(B) if (world == 1 and a.items == 10_000_000 and a.dim == 128 and a.k == 100) else (None, None)
+        extra = {"traffic": traffic, "traffic_unit": "bytes per step, dram read+write of all filter launches (ncu)",
+                 "traffic_source": src, "algorithmic_bytes": byt, "kernel": "score_filter_tc_kernel",
+                 "ms_per_step": filt_ms_per_step}
         if B >= 256:
             flops = 2.0 * B * rows * a.dim
             ach = flops / (filt_ms_per_step * 1e-3) / 1e12
-            return {"bound": "tensor", "achieved": ach, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tc_sustained"], "traffic": None, "basis": pk["basis"] + " (sustained bf16)",
-                    "kernel": "score_filter_tc_kernel", "ms_per_step": filt_ms_per_step}
-        byt = rows * d_pad * 2.0 + B * a.dim * 4.0 + B * a.k * 8.0
+            return dict({"bound": "tensor", "achieved": ach, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tc_sustained"], "basis": pk["basis"] + " (sustained bf16)",
+                         "algorithmic_flops": flops}, **extra)
         ach = byt / (filt_ms_per_step * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "basis": pk["basis"] + " (copy bandwidth)", "kernel": "score_filter_tc_kernel",
-                "ms_per_step": filt_ms_per_step}
+        return dict({"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                     "basis": pk["basis"] + " (copy bandwidth)"}, **extra)
 
     # ---- headline: device-resident throughput (events on the launching stream), clocks sampled meanwhile
     sampler = ClockSampler(local) if rank == 0 else None
