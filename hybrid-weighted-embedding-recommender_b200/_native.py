@@ -45,6 +45,7 @@ SIGNATURES = {
     "hwer_peer_close": (c_int, [c_void_p]),
     "hwer_peer_free": (c_int, [c_void_p]),
     "hwer_exchange_create": (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p), c_int32]),
+    "hwer_exchange_configure": (c_int, [c_void_p, c_int64, c_int32]),
     "hwer_exchange_destroy": (c_int, [c_void_p]),
     "hwer_topk_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_uint32, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_int32, c_void_p]),

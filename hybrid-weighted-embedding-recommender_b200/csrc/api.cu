@@ -275,7 +275,7 @@ namespace {
 // each query's result into the exchange buffer of the GPU that merges it instead of the local out arrays.
 int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
               int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev,
-              const hwer::PeerDst* peer, void* stream_v) {
+              const hwer::PeerDst* peer, const hwer::ExchangeView* xv, unsigned int call_epoch, void* stream_v) {
     if (!ix || B < 0 || k <= 0 || (B > 0 && (!queries_dev || (!peer && (!out_idx_dev || !out_score_dev)))))
         return fail(HWER_E_INVALID, "hwer_topk: bad argument");
     if (mode != HWER_MODE_EXACT && mode != HWER_MODE_BF16) return fail(HWER_E_INVALID, "hwer_topk: unknown mode");
@@ -302,8 +302,16 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
     const float eps_rel = ix->use_tc ? hwer::bf16_score_eps_rel(ix->d_pad) : hwer::f32_score_eps_rel(ix->d);
     const float margin_factor = 2.0f * eps_rel * ix->max_norm * 1.0001f;
     const long long T = ix->n_tiles;
+    // Sharded catalogue: every rank walks the SAME round schedule (that of the largest shard) because the rounds
+    // exchange thresholds; a rank whose shard is a tile shorter simply scores an empty range in the last round.
+    const bool share_thr = xv && xv->world > 1;
+    long long T_sched = T;
+    if (share_thr && xv->sched_rows > 0) T_sched = (xv->sched_rows + hwer::kTileItems - 1) / hwer::kTileItems;
+    if (T_sched < T) T_sched = T;
+    const int k_share = share_thr ? (k + xv->world - 1) / xv->world : k;
+    int chunk_idx = 0;
 
-    for (long long q0 = 0; q0 < B; q0 += (long long)chunk) {
+    for (long long q0 = 0; q0 < B; q0 += (long long)chunk, ++chunk_idx) {
         const int Bc = (int)(((long long)B - q0) < (long long)chunk ? ((long long)B - q0) : (long long)chunk);
         const float* Q = queries_dev + (size_t)q0 * ix->d;
         HWER_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(unsigned int) * Bc, stream));
@@ -314,12 +322,14 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         ix->other_launches += 3;   // fill + margin/floor + final
         long long seen = 0;
         int round = 0;
-        while (seen < T) {
+        while (seen < T_sched) {
             long long take = round == 0 ? sch.first_tiles : seen * (seen >= sch.late_tiles ? 1 : sch.growth);
-            long long end = seen + take;
-            if (end > T || (T - end) * 4 < take) end = T;          // absorb a short remainder into this round ...
-            if (round == 0 && end * hwer::kTileItems > (long long)sch.cap)   // ... unless the dense round would
-                end = seen + take < T ? seen + take : T;                      // outgrow the candidate lists
+            long long end_s = seen + take;
+            if (end_s > T_sched || (T_sched - end_s) * 4 < take) end_s = T_sched;   // absorb a short remainder ...
+            if (round == 0 && end_s * hwer::kTileItems > (long long)sch.cap)        // ... unless the dense round would
+                end_s = seen + take < T_sched ? seen + take : T_sched;              // outgrow the candidate lists
+            const long long end = end_s < T ? end_s : T;                            // this shard's share of the round
+            const long long seen_l = seen < T ? seen : T;
             const bool timed = prof_begin(ix, stream);
             if (ix->use_tc) {
                 hwer::FilterParams p;
@@ -330,23 +340,42 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 if (nq > nq_max) nq = nq_max;
                 p.nq = nq; p.nqb = (Bc + nq - 1) / nq;
                 p.thr = ix->thr; p.floor = ix->floor; p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
-                p.n_items = ix->n; p.tile_begin = (int)seen; p.tile_end = (int)end;
+                p.n_items = ix->n; p.tile_begin = (int)seen_l; p.tile_end = (int)end;
                 p.tile_mul = ix->tile_mul; p.tile_mod = T;
                 p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics
                 HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
             } else {
-                long long rb = seen * hwer::kTileItems, re = end * hwer::kTileItems;
+                long long rb = seen_l * hwer::kTileItems, re = end * hwer::kTileItems;
                 if (re > ix->n) re = ix->n;
                 HWER_CUDA(hwer::launch_filter_simt(ix->table, ix->n, ix->d, Q, Bc, ix->thr, ix->cand, ix->cnt, sch.cap,
                                                    rb, re, ix->num_sms, stream));
             }
             prof_end(ix, stream, timed);
-            const int fixed = (ix->use_tc && round == 0) ? (int)((end - seen) * hwer::kTileItems) : -1;
-            HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
-                                                  ix->needed_dev, stream));
+            const int fixed = (ix->use_tc && round == 0) ? (int)((end - seen_l) * hwer::kTileItems) : -1;
+            if (share_thr) {
+                // each shard publishes its ceil(k/G)-th best score so far to every peer; the min over shards bounds
+                // the global k-th best from below (DESIGN.md "Multi-GPU"), so all shards filter with ~1/G the hits
+                hwer::SelExchange sx;
+                memset(&sx, 0, sizeof sx);
+                sx.world = xv->world; sx.rank = xv->rank; sx.b_cap = xv->b_cap; sx.parity = round & 1; sx.q0 = q0;
+                sx.epoch = (call_epoch * 64u + (unsigned int)chunk_idx) * 64u + (unsigned int)round + 1u;
+                sx.flags = xv->flags[xv->rank];
+                for (int r = 0; r < xv->world; ++r) sx.thr_x[r] = xv->thr_x[r];
+                sx.mode = hwer::kSelKthToPeers;
+                HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k_share, fixed, margin, ix->thr,
+                                                      ix->needed_dev, &sx, stream));
+                HWER_CUDA(hwer::launch_exchange_signal(*xv, 4, sx.epoch, stream));
+                sx.mode = hwer::kSelCompactMin;
+                HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
+                                                      ix->needed_dev, &sx, stream));
+                ix->other_launches += 2;
+            } else {
+                HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
+                                                      ix->needed_dev, nullptr, stream));
+            }
             ix->filter_launches += 1;
             ix->other_launches += 1;
-            seen = end;
+            seen = end_s;
             ++round;
         }
         hwer::PeerDst pd;
@@ -366,6 +395,7 @@ struct hwer_exchange {
     hwer::ExchangeView v;
     unsigned int epoch = 0;
     int device = 0;
+    bool share_thresholds = true;
 };
 
 namespace {
@@ -373,7 +403,7 @@ namespace {
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct ExchangeLayout {
-    size_t flags, xs, xi, out_idx, out_score64, out_score, total;
+    size_t flags, xs, xi, out_idx, out_score64, out_score, thr_x, total;
     int q_cap;
 };
 
@@ -388,6 +418,7 @@ ExchangeLayout exchange_layout(int world, int b_cap, int k_cap) {
     L.out_idx = off; off += align256(o * 8);
     L.out_score64 = off; off += align256(o * 8);
     L.out_score = off; off += align256(o * 4);
+    L.thr_x = off; off += align256((size_t)2 * world * b_cap * sizeof(float));
     L.total = off;
     return L;
 }
@@ -399,7 +430,7 @@ extern "C" {
 int hwer_topk(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
               int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream_v) {
     return topk_impl(ix, queries_dev, B, k, mode, cap, idx_offset, out_idx_dev, out_score_dev, out_score64_dev, nullptr,
-                     stream_v);
+                     nullptr, 0u, stream_v);
 }
 
 int64_t hwer_exchange_bytes(int32_t world, int32_t b_cap, int32_t k_cap) {
@@ -463,9 +494,17 @@ int hwer_exchange_create(hwer_exchange_t** out, int32_t world, int32_t rank, int
         x->v.out_idx[r] = reinterpret_cast<long long*>(b + L.out_idx);
         x->v.out_score64[r] = reinterpret_cast<double*>(b + L.out_score64);
         x->v.out_score[r] = reinterpret_cast<float*>(b + L.out_score);
+        x->v.thr_x[r] = reinterpret_cast<float*>(b + L.thr_x);
     }
     x->device = device;
     *out = x;
+    return HWER_OK;
+}
+
+int hwer_exchange_configure(hwer_exchange_t* x, int64_t largest_shard_rows, int32_t share_thresholds) {
+    if (!x || largest_shard_rows < 0) return fail(HWER_E_INVALID, "hwer_exchange_configure: bad argument");
+    x->v.sched_rows = largest_shard_rows;
+    x->share_thresholds = share_thresholds != 0;
     return HWER_OK;
 }
 
@@ -496,7 +535,9 @@ int hwer_topk_sharded(hwer_index_t* ix, hwer_exchange_t* x, const float* queries
     memset(&pd, 0, sizeof pd);
     pd.world = x->v.world; pd.rank = x->v.rank; pd.q_per_owner = x->v.q_per_owner; pd.q_cap = x->v.q_cap; pd.k_cap = x->v.k_cap;
     for (int r = 0; r < x->v.world; ++r) { pd.xs[r] = x->v.xs[r]; pd.xi[r] = x->v.xi[r]; }
-    int rc = topk_impl(ix, queries_dev, B, k, mode, cap, idx_offset, nullptr, nullptr, nullptr, &pd, stream_v);
+    int rc = topk_impl(ix, queries_dev, B, k, mode, cap, idx_offset, nullptr, nullptr, nullptr, &pd,
+                       // tiny batches are launch-bound, not hit-bound: the two extra launches per round do not pay
+                       (x->share_thresholds && B > 16) ? &x->v : nullptr, epoch, stream_v);
     if (rc) return rc;
     HWER_CUDA(hwer::launch_exchange_signal(x->v, 0, epoch, stream));
     if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));

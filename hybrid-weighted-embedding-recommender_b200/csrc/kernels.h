@@ -11,6 +11,7 @@ constexpr int kTileItems = 128;      // catalogue rows per tcgen05 tile (UMMA M)
 constexpr int kKBlock = 64;          // bf16 elements per 128-byte swizzled smem row
 constexpr int kMaxNQ = 256;          // queries per CTA-resident query block (UMMA N)
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kMaxPeers = 8;         // GPUs of one node
 
 // Proven bound on |bf16-tensor-core score - exact score| / (|q| * |x|):
 // two round-to-nearest bf16 roundings (2^-9 each) plus fp32 accumulation of
@@ -61,13 +62,29 @@ cudaError_t launch_query_margin(const float* queries, int B, int d, float factor
                                 float* floor, cudaStream_t stream);
 cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream);
 
+// Cross-GPU threshold sharing for a row-sharded catalogue (DESIGN.md "Multi-GPU"): with G shards, the min over
+// shards of each shard's ceil(K/G)-th best score so far is a lower bound of the GLOBAL K-th best, and a much
+// tighter one than a shard's own K-th best -- so every shard admits ~1/G as many candidates per round.
+//   kSelKthToPeers : select the kth best of the local list and store it (no margin) into every peer's thr_x slot
+//   kSelCompactMin : wait for every shard's value of this round, thr = min - margin, compact the local list
+enum : int { kSelLocal = 0, kSelKthToPeers = 1, kSelCompactMin = 2 };
+struct SelExchange {
+    int mode;                        // kSelLocal: no exchange (single GPU)
+    int world, rank;
+    int b_cap;                       // row length of thr_x
+    int parity;                      // rounds alternate between two halves of thr_x
+    long long q0;                    // global query index of this launch's first query
+    unsigned int epoch;              // flags[32 + g] >= epoch <=> shard g has published this round's values
+    float* thr_x[kMaxPeers];         // per rank: [2][world][b_cap]
+    unsigned int* flags;             // this rank's flag block
+};
+
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
-                                  cudaStream_t stream);
+                                  const SelExchange* sx, cudaStream_t stream);
 
 // Where final_kernel stores a query's result when the catalogue is sharded over several GPUs: straight into the
 // exchange buffer of the GPU that owns (merges) that query, over NVLink peer stores (exchange.cu).
-constexpr int kMaxPeers = 8;
 struct PeerDst {
     int world;                       // 0 = disabled (results go to the local out_* arrays)
     int rank;
@@ -88,7 +105,9 @@ cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt
 // of the merged rows to every rank; final wait + copy-out.
 struct ExchangeView {
     int world, rank, q_per_owner, q_cap, k_cap, b_cap;
-    unsigned int* flags[kMaxPeers];      // per rank: [2][kMaxPeers] epochs + [16] scratch (counter, error)
+    unsigned int* flags[kMaxPeers];      // per rank: [2][kMaxPeers] epochs, [16] counter, [17] error, [32..39] threshold epochs
+    float* thr_x[kMaxPeers];             // per rank: [2][world][b_cap] shared-threshold slots
+    long long sched_rows;                // rows of the largest shard: every rank walks the same round schedule
     double* xs[kMaxPeers];
     long long* xi[kMaxPeers];
     long long* out_idx[kMaxPeers];       // per rank: [b_cap, k_cap] merged rows (row stride k of the call)

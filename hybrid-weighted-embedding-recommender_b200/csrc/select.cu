@@ -54,17 +54,46 @@ __device__ __forceinline__ void hist_add_aggregated(unsigned int* hist, bool tak
     if (take) atomicAdd(&hist[bin], 1u);
 }
 
+__device__ __forceinline__ unsigned int sel_ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until shard `g` has published this round's thresholds (bounded: a dead peer must not hang the GPU).
+__device__ bool sel_wait_shard(const SelExchange& sx, int g) {
+    const long long t0 = clock64();
+    while ((int)(sel_ld_acquire_sys(sx.flags + 32 + g) - sx.epoch) < 0) {
+        if (clock64() - t0 > 6000000000ll) { atomicExch(sx.flags + 17, 1u); return false; }
+        __nanosleep(100);
+    }
+    return true;
+}
+__device__ __forceinline__ float sel_global_kth(const SelExchange& sx, long long q) {
+    float t = __int_as_float(0x7f800000);
+    for (int g = 0; g < sx.world; ++g)
+        t = fminf(t, __ldcv(sx.thr_x[sx.rank] + ((size_t)sx.parity * sx.world + g) * sx.b_cap + q));
+    return t;
+}
+__device__ __forceinline__ void sel_publish_kth(const SelExchange& sx, long long q, float sk) {
+    for (int g = 0; g < sx.world; ++g)
+        sx.thr_x[g][((size_t)sx.parity * sx.world + sx.rank) * sx.b_cap + q] = sk;
+}
+
 // K-th largest key prefix by radix select (4 passes x 8 bits over the order-preserving score image), then an
 // unordered compaction of everything at or above the new threshold.  O(c) work per query; a full sort of the
 // list is only needed once, in final_kernel, over the ~1.4 K survivors.
 __global__ void __launch_bounds__(kSelThreads)
 select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap, int K,
                       int fixed_count, const float* __restrict__ margin, float* __restrict__ thr,
-                      unsigned int* needed_cap) {
+                      unsigned int* needed_cap, const __grid_constant__ SelExchange sx) {
     extern __shared__ unsigned long long keys[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sel_prefix, sel_remaining, kept_s, valid_s;
     const int q = blockIdx.x;
+    if (sx.mode == kSelCompactMin) {
+        if ((int)threadIdx.x < sx.world) sel_wait_shard(sx, threadIdx.x);
+        __syncthreads();
+    }
     unsigned int c_raw = fixed_count >= 0 ? (unsigned int)fixed_count : cnt[q];
     if (c_raw > cap) {
         if (threadIdx.x == 0) atomicMax(needed_cap, c_raw);
@@ -84,7 +113,14 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
     if (lane_id() == 0 && nvalid) atomicAdd(&valid_s, nvalid);
     __syncthreads();
     float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
-    if ((int)valid_s >= K) {
+    if (sx.mode == kSelCompactMin) {
+        const float sk = sel_global_kth(sx, sx.q0 + q);          // lower bound of the global K-th best score
+        if (sk > __int_as_float(0xff800000)) {
+            const float m = margin ? margin[q] : 0.0f;
+            t = sk - m;
+            if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);
+        }
+    } else if ((int)valid_s >= K) {
         unsigned int mask = 0u;
         for (int shift = 24; shift >= 0; shift -= 8) {
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
@@ -131,6 +167,11 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
         const float m = margin ? margin[q] : 0.0f;
         t = sk - m;
         if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
+        if (sx.mode == kSelKthToPeers) t = sk;
+    }
+    if (sx.mode == kSelKthToPeers) {                  // K here is ceil(k / shards); -inf = "cannot bound yet"
+        if (threadIdx.x == 0) sel_publish_kth(sx, sx.q0 + q, t);
+        return;
     }
     for (int base = 0; base < c; base += blockDim.x) {
         const int i = base + threadIdx.x;
@@ -159,12 +200,16 @@ constexpr int kSelWarpKeys = 1024;          // keys staged per warp (8 KB); long
 __global__ void __launch_bounds__(kSelWarps * 32)
 select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap,
                            int B, int K, const float* __restrict__ margin, float* __restrict__ thr,
-                           unsigned int* needed_cap) {
+                           unsigned int* needed_cap, const __grid_constant__ SelExchange sx) {
     __shared__ unsigned long long keys_all[kSelWarps][kSelWarpKeys];
     __shared__ unsigned int hist_all[kSelWarps][256];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int q = blockIdx.x * kSelWarps + w;
     if (q >= B) return;
+    if (sx.mode == kSelCompactMin) {
+        if (l < sx.world) sel_wait_shard(sx, l);
+        __syncwarp();
+    }
     unsigned int* hist = hist_all[w];
     unsigned int c_raw = cnt[q];
     if (c_raw > cap) {
@@ -185,7 +230,14 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
     __syncwarp();
     for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
     float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
-    if ((int)nvalid >= K) {
+    if (sx.mode == kSelCompactMin) {
+        const float sk = sel_global_kth(sx, sx.q0 + q);          // lower bound of the global K-th best score
+        if (sk > __int_as_float(0xff800000)) {
+            const float m = margin ? margin[q] : 0.0f;
+            t = sk - m;
+            if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);
+        }
+    } else if ((int)nvalid >= K) {
         unsigned int mask = 0u, prefix = 0u, remaining = (unsigned int)K;
         for (int shift = 24; shift >= 0; shift -= 8) {
 #pragma unroll
@@ -233,6 +285,11 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
         const float m = margin ? margin[q] : 0.0f;
         t = sk - m;
         if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
+        if (sx.mode == kSelKthToPeers) t = sk;
+    }
+    if (sx.mode == kSelKthToPeers) {                  // K here is ceil(k / shards); -inf = "cannot bound yet"
+        if (l == 0) sel_publish_kth(sx, sx.q0 + q, t);
+        return;
     }
     unsigned int kept = 0u;
     for (int base = 0; base < c; base += 32) {
@@ -439,11 +496,13 @@ inline size_t pow2_ge(size_t v) {
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
-                                  cudaStream_t stream) {
+                                  const SelExchange* sxp, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
+    SelExchange sx;
+    if (sxp) sx = *sxp; else memset(&sx, 0, sizeof sx);
     if (fixed_count < 0 && B >= 128) {      // filter rounds of large batches: short lists, one warp per query
         select_compact_warp_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(
-            cand, cnt, cap, B, K, margin, thr, needed_cap);
+            cand, cnt, cap, B, K, margin, thr, needed_cap, sx);
         return cudaGetLastError();
     }
     // stage only what can be there: a dense round holds fixed_count keys, a filter round at most cap
@@ -451,7 +510,7 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
     const size_t smem = (n < 1024 ? 1024 : n) * sizeof(unsigned long long);
     cudaError_t e = set_smem(select_compact_kernel, smem);
     if (e != cudaSuccess) return e;
-    select_compact_kernel<<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, fixed_count, margin, thr, needed_cap);
+    select_compact_kernel<<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, fixed_count, margin, thr, needed_cap, sx);
     return cudaGetLastError();
 }
 

@@ -79,6 +79,9 @@ class PeerExchange:
                                              self.device.index or 0))
         dist.barrier(group=group)          # every rank has opened every buffer before anyone stores into one
 
+    def configure(self, largest_shard_rows: int, share_thresholds: bool = True):
+        N.check(N.lib().hwer_exchange_configure(self._h, int(largest_shard_rows), 1 if share_thresholds else 0))
+
     def check(self):
         """Synchronises the current stream; raises if a wait on a peer GPU timed out."""
         with torch.cuda.device(self.device):
@@ -111,11 +114,22 @@ class ShardedTopK:
     through the peer-memory exchange (`exchange="p2p"`, the default on a multi-GPU node) or through one NCCL
     all-gather + local merge (`exchange="nccl"`)."""
 
-    def __init__(self, local_table, row_offset: int, shadow=None, group=None, max_norm=None, exchange="auto"):
+    def __init__(self, local_table, row_offset: int, shadow=None, group=None, max_norm=None, exchange="auto",
+                 share_thresholds=True):
         self.group = group
         self.row_offset = int(row_offset)
+        self.rows_max = int(local_table.shape[0])
+        if dist.is_initialized() and dist.get_world_size(group) > 1 and local_table.is_cuda:
+            # the admission margin scales with the largest row norm of the WHOLE catalogue, and all ranks walk the
+            # round schedule of the largest shard (hwer_exchange_configure): agree on both once
+            if max_norm is None:
+                max_norm = ops.norm_stats(local_table)[4]
+            t = torch.tensor([float(max_norm), float(self.rows_max)], dtype=torch.float64, device=local_table.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            max_norm, self.rows_max = float(t[0].item()), int(t[1].item())
         self.index = ops.TopKIndex(local_table, shadow, max_norm=max_norm)
         self.exchange = exchange
+        self.share_thresholds = bool(share_thresholds)
         self._px = None
 
     def local_topk(self, queries, k, mode="exact"):
@@ -128,6 +142,7 @@ class ShardedTopK:
             if self._px is not None:
                 self._px.close()
             self._px = PeerExchange(max(B, 256), k, self.index.device, self.group)
+            self._px.configure(self.rows_max, self.share_thresholds)
         return self._px
 
     def topk_p2p_async(self, queries, k, mode="exact", cap=0, want_f64=False):

@@ -126,6 +126,12 @@ int hwer_peer_close(void* dev_ptr);
 int hwer_peer_free(void* dev_ptr);
 int hwer_exchange_create(hwer_exchange_t** out, int32_t world, int32_t rank, int32_t b_cap, int32_t k_cap,
                          void* const* bases /* [world] device pointers */, int32_t device);
+/* largest_shard_rows: rows of the largest shard over all ranks (every rank must pass the same value: the ranks walk
+ * one common round schedule because, with share_thresholds != 0 (default), every round exchanges per-query
+ * thresholds -- each shard publishes its ceil(k/G)-th best score so far, the min over shards bounds the global
+ * k-th best from below, so a shard admits ~1/G as many candidates per round.  0 = the shards are known to be of
+ * equal size (same number of 128-row tiles). */
+int hwer_exchange_configure(hwer_exchange_t* exchange, int64_t largest_shard_rows, int32_t share_thresholds);
 int hwer_exchange_destroy(hwer_exchange_t* exchange);
 #define HWER_PHASE_SEARCH 1  /* local search; its last kernel stores into the owners' buffers; publish "scattered" */
 #define HWER_PHASE_MERGE 2   /* wait for every source, merge the owned queries, deliver to every rank, publish      */

@@ -401,21 +401,25 @@ class _Exchange:
         self._h = h
 
 
-@pytest.mark.parametrize("world,B,k", [(2, 50, 100), (3, 7, 10), (1, 33, 20)])
-def test_peer_exchange_protocol_on_one_gpu(hw, world, B, k):
+# (one GPU plays every rank here, so batches stay small: a rank's waiting kernels must leave SMs free for the kernels
+#  of the ranks it waits for -- with one GPU per rank, as deployed, that coupling does not exist)
+@pytest.mark.parametrize("world,B,k,share", [(2, 50, 100, 1), (3, 7, 10, 1), (1, 33, 20, 1), (3, 40, 100, 1),
+                                             (2, 50, 100, 0), (3, 9, 10, 0)])
+def test_peer_exchange_protocol_on_one_gpu(hw, world, B, k, share):
     """hwer_topk_sharded with `world` ranks living in ONE process: one exchange buffer, index (a row shard) and
-    stream per rank.  Exercises the real protocol -- final kernel storing into the owner's buffer, release/acquire
-    flags, owner merge delivering to every rank, collect -- and must reproduce the single-index answer bit for bit
-    on every rank, twice (buffer reuse across epochs)."""
+    stream per rank.  Exercises the real protocol -- per-round threshold sharing (share=1), final kernel storing
+    into the owner's buffer, release/acquire flags, owner merge delivering to every rank, collect -- and must
+    reproduce the single-index answer bit for bit on every rank, twice (buffer reuse across epochs)."""
     import ctypes
     from hwer_b200 import _native as N
     lib = N.lib()
-    n, d = 30000, 128
+    n, d = 30011, 128                                    # shards of unequal size: a common round schedule matters
     t_np, t = unit_table(n, d, 91)
     t_np[20000:20003] = t_np[5]                          # ties across shard boundaries
     t = torch.from_numpy(t_np).cuda()
-    whole = hw.ops.TopKIndex(t)
-    nbytes = lib.hwer_exchange_bytes(world, 256, k)
+    whole = hw.ops.TopKIndex(t, max_norm=1.0001)
+    b_cap = max(256, B)
+    nbytes = lib.hwer_exchange_bytes(world, b_cap, k)
     assert nbytes > 0
     bases = (ctypes.c_void_p * world)()
     handle = (ctypes.c_ubyte * N.IPC_HANDLE_BYTES)()
@@ -426,10 +430,12 @@ def test_peer_exchange_protocol_on_one_gpu(hw, world, B, k):
     ex, shards, streams = [], [], []
     for r in range(world):
         h = ctypes.c_void_p()
-        N.check(lib.hwer_exchange_create(ctypes.byref(h), world, r, 256, k, bases, 0))
+        N.check(lib.hwer_exchange_create(ctypes.byref(h), world, r, b_cap, k, bases, 0))
+        rows_max = max(hw.sharded.partition(n, world, g)[1] - hw.sharded.partition(n, world, g)[0] for g in range(world))
+        N.check(lib.hwer_exchange_configure(h, rows_max, share))
         ex.append(_Exchange(h))
         b, e = hw.sharded.partition(n, world, r)
-        shards.append((hw.ops.TopKIndex(t[b:e].contiguous()), b))
+        shards.append((hw.ops.TopKIndex(t[b:e].contiguous(), max_norm=1.0001), b))
         shards[-1][0].topk(t[:B].contiguous(), k)        # sizes the workspace now (growing it synchronises the device)
         streams.append(torch.cuda.Stream())
     try:
