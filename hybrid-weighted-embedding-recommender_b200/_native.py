@@ -58,6 +58,7 @@ SIGNATURES = {
                                c_void_p]),
     "hwer_eval_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "hwer_link_metrics": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -702,4 +702,12 @@ int hwer_eval_metrics(const int64_t* topk_dev, int32_t U, int32_t kret, const in
     return HWER_OK;
 }
 
+int hwer_link_metrics(const float* scores_dev, const uint8_t* labels_dev, int64_t P, float threshold, double* out8_dev,
+                      void* stream) {
+    if (!scores_dev || !labels_dev || !out8_dev || P <= 0 || P >= (1LL << 31) - 1)
+        return fail(HWER_E_INVALID, "hwer_link_metrics: bad argument (0 < P < 2^31 - 1)");
+    HWER_CUDA(hwer::launch_link_metrics(scores_dev, labels_dev, P, threshold, out8_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
 }  // extern "C"

@@ -143,6 +143,10 @@ cudaError_t launch_eval_reduce(const double* per_user, int U, int M, const long 
                                const unsigned int* seen_bitmap, long long n_items, int n_cut, double* out,
                                cudaStream_t stream);
 
+// Link-prediction metrics (link_metrics.cu): out8 = ap, precision, recall, accuracy, tp, fp, fn, tn.
+cudaError_t launch_link_metrics(const float* score, const unsigned char* label, long long P, float thr, double* out8,
+                                cudaStream_t stream);
+
 // NCF re-rank (ncf.cu): params = [W1 (out x in, row-major), b1, ..., W_depth, b_depth, w_out (F), b_out (1)].
 int ncf_layer_in(int F, int depth, int layer);
 int ncf_layer_out(int F, int depth, int layer);

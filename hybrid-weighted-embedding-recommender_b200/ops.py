@@ -304,3 +304,20 @@ def eval_metrics(topk_items, train_ptr, train_idx, val_ptr, val_idx, val_rel, cu
                                           _dev_ptr(val_ptr), _dev_ptr(val_idx), _dev_ptr(val_rel), _dev_ptr(cut),
                                           n_cut, int(n_items), _dev_ptr(out), _dev_ptr(pu), _stream(dev)))
     return (out, pu) if per_user else out
+
+
+LINK_METRIC_NAMES = ("ap", "precision", "recall", "accuracy", "tp", "fp", "fn", "tn")
+
+
+def link_metrics(scores, labels, threshold=0.5):
+    """Average precision and precision / recall / accuracy at `threshold` of scored 0/1-labelled pairs, on the
+    device (the sklearn calls of hwer/validation.py:52-59).  Returns a float64 tensor of 8, see LINK_METRIC_NAMES."""
+    scores = _need(scores, torch.float32, "scores", 1)
+    labels = _need(labels, torch.uint8, "labels", 1)
+    if labels.shape[0] != scores.shape[0] or scores.shape[0] == 0:
+        raise ValueError("link_metrics: scores and labels must be non-empty and of equal length")
+    out = torch.empty(8, dtype=torch.float64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        N.check(N.lib().hwer_link_metrics(_dev_ptr(scores), _dev_ptr(labels), scores.shape[0], float(threshold),
+                                          _dev_ptr(out), _stream(scores.device)))
+    return out

@@ -30,9 +30,12 @@ class ContentRecommendation(RecommendationBase):
         self.embedding_mapper = embedding_mapper
 
     def fit(self, nodes: List[Node], edges: List[Edge], node_data: Dict[Node, Dict[FeatureName, object]] = None,
-            vectors=None, **kwargs):
+            vectors=None, hyperparameters=None, **kwargs):
         """`vectors`: the finished [N, n_dims] unit-norm content table (what __build_content_embeddings__
-        produces in the reference), row i belonging to nodes[i]."""
+        produces in the reference), row i belonging to nodes[i].  It may also arrive as hyperparameters["vectors"]
+        (the keyword validation.test_algorithm passes, hwer/validation.py:197,202)."""
+        if vectors is None and hyperparameters:
+            vectors = hyperparameters.get("vectors")
         if vectors is None:
             raise ValueError("hwer_b200 serves trained tables: pass vectors=<[N, d] unit-norm array>")
         super().fit(nodes, edges, node_data, **kwargs)
@@ -104,7 +107,12 @@ class GcnNCF(RecommendationBase):
         return table.cpu().numpy()
 
     def fit(self, nodes: List[Node], edges: List[Edge], node_data: Dict[Node, Dict[FeatureName, object]] = None,
-            content_vectors=None, collaborative_vectors=None, alpha=None, **kwargs):
+            content_vectors=None, collaborative_vectors=None, alpha=None, hyperparameters=None, **kwargs):
+        if hyperparameters:      # the keyword validation.test_algorithm passes (hwer/validation.py:197,202)
+            content_vectors = hyperparameters.get("content_vectors") if content_vectors is None else content_vectors
+            if collaborative_vectors is None:
+                collaborative_vectors = hyperparameters.get("collaborative_vectors")
+            alpha = hyperparameters.get("alpha") if alpha is None else alpha
         if collaborative_vectors is None:
             raise ValueError("hwer_b200 serves trained tables: pass collaborative_vectors=<[N, d] array>")
         super().fit(nodes, edges, node_data, **kwargs)

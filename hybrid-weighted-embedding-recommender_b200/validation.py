@@ -3,13 +3,19 @@
   model_get_topk_gpu        replaces model_get_topk_knn          hwer/validation.py:30-35 (hook alias :38)
   extraction_efficiency     same signature and `metrics` keys    hwer/validation.py:100-187
   ncf_eval                  1 positive + 100 sampled negatives   hwer/validation.py:68-97
+  link_prediction_accuracy  10x sampled negative pairs           hwer/validation.py:41-65
+  get_prediction_details, test_algorithm, test_multiple_algorithms, display_results, run_model_for_hpo,
+  run_models_for_testing    the harness around them              hwer/validation.py:190-309
 The per-user Python loops over reciprocal_rank / ndcg / recall (hwer/utils.py:71-121) become one
-hwer_eval_metrics launch; pair scores come from hwer_pair_score.
+hwer_eval_metrics launch; pair scores come from hwer_pair_score (or hwer_ncf_score); the sklearn metric calls of
+link_prediction_accuracy become one hwer_link_metrics launch per pair set.
 """
+import copy
+import datetime
 import random
 import time
 from collections import defaultdict
-from typing import Dict, List, Tuple
+from typing import Any, Dict, List, Set, Tuple
 
 import numpy as np
 import torch
@@ -126,3 +132,151 @@ def extraction_efficiency(model, train_edges: List[Edge], validation_edges: List
                "recall@10": m["recall@10"],
                "diversity": m["distinct_items"] / max(len(all_items), 1), **ncf_metrics}
     return {"users": all_users, "rows": rows, "scores": scores, "metrics": metrics, "all_metrics": m}
+
+
+def link_prediction_accuracy(model: RecommendationBase, nodes: List[Node], train_edges: List[Edge],
+                             validation_edges: List[Edge]):
+    """hwer/validation.py:41-65.  The negative pairs are drawn on the host with random.choices in the reference's
+    order (train src, train dst, validation src, validation dst), so `random.seed` reproduces its pair sets; the
+    pair scores and every metric are computed on the device."""
+    m = 10
+    sets = []
+    for edges in (train_edges, validation_edges):
+        neg_src = random.choices(nodes, k=len(edges) * m)
+        neg_dst = random.choices(nodes, k=len(edges) * m)
+        sets.append(([e.src for e in edges] + neg_src, [e.dst for e in edges] + neg_dst, len(edges)))
+    results = {}
+    for name, (src, dst, n_pos) in zip(("train", "val"), sets):
+        if len(src) == 0:
+            raise ValueError("link_prediction_accuracy: empty %s edge list" % name)
+        scores = model.predict_rows(model._rows_of(src), model._rows_of(dst))
+        labels = torch.zeros(len(src), dtype=torch.uint8, device=scores.device)
+        labels[:n_pos] = 1
+        ap, precision, recall, accuracy = ops.link_metrics(scores.float().contiguous(), labels)[:4].tolist()
+        results["lp_%s_ap" % name] = ap
+        results["lp_%s_precision" % name] = precision
+        results["lp_%s_recall" % name] = recall
+        results["lp_%s_accuracy" % name] = accuracy
+    return results
+
+
+def get_prediction_details(recsys, nodes: List[Node], train_affinities: List[Edge], validation_affinities: List[Edge],
+                           model_get_topk=None, node_type: NodeType = "item"):
+    """hwer/validation.py:258-275."""
+    def get_details(recsys, affinities):
+        predictions = np.array(recsys.predict([(u, i) for u, i, r in affinities]))
+        if np.sum(np.isnan(predictions)) > 0:
+            count = np.sum(np.isnan(predictions))
+            raise AssertionError("Encountered Nan Predictions = %s" % count,
+                                 np.array(affinities)[np.isnan(predictions)])
+        actuals = np.array([r for u, i, r in affinities])
+        return predictions, actuals
+
+    predictions, actuals = get_details(recsys, validation_affinities)
+    train_predictions, _ = get_details(recsys, train_affinities)
+    ex_ee = extraction_efficiency(recsys, train_affinities, validation_affinities, model_get_topk, node_type)
+    lp_res = link_prediction_accuracy(recsys, nodes, train_affinities, validation_affinities)
+    lp_res.update(ex_ee["metrics"])
+    return predictions, actuals, lp_res
+
+
+def test_algorithm(train_affinities: List[Edge], validation_affinities: List[Edge],
+                   nodes: List[Node], node_types: Set[NodeType], hyperparameters,
+                   get_data_mappers, algo, node_type: NodeType):
+    """hwer/validation.py:190-222.  Training is outside this package: `hyperparameters` carries the trained tables
+    (`vectors` for algo "content"; `collaborative_vectors` [+ `content_vectors`, `alpha`] for "gcn_ncf") next to
+    `n_dims`; fit() picks them up from its `hyperparameters` keyword."""
+    from . import GcnNCF, ContentRecommendation
+    embedding_mapper, node_data = get_data_mappers()
+    kwargs = dict(hyperparameters=copy.copy(hyperparameters))
+    algo_map = dict(gcn_ncf=GcnNCF, content=ContentRecommendation)
+    recsys = algo_map[algo](embedding_mapper=embedding_mapper, node_types=node_types, n_dims=hyperparameters["n_dims"])
+
+    start = time.time()
+    _ = recsys.fit(nodes, train_affinities, node_data, **kwargs)
+    end = time.time()
+    total_time = end - start
+
+    rnode = Node(list(node_types)[0], "eifjcchchbniufclvfdugvhnftdvjculhjitjihuncce")
+    rnode2 = Node(list(node_types)[0], "eifjcchchbnirdjknkrvtfkbfurvjdfjhllbddtbvicb")
+    default_preds = recsys.predict([(train_affinities[0].src, rnode),
+                                    (train_affinities[0].src, train_affinities[0].dst),
+                                    (rnode, rnode2),
+                                    (rnode2, train_affinities[0].src)])
+    print("Default Preds = ", default_preds)
+    assert np.sum(np.isnan(default_preds)) == 0
+
+    res2 = {"algo": algo, "time": total_time}
+    predictions, actuals, stats = get_prediction_details(recsys, nodes, train_affinities, validation_affinities,
+                                                         model_get_topk, node_type)
+    res2.update(stats)
+    results = [res2]
+    return recsys, results, predictions, actuals
+
+
+test_algorithm.__test__ = False      # a harness entry point named like the reference's, not a pytest test
+
+
+def test_multiple_algorithms(train_affinities, validation_affinities, nodes: List[Node], node_types: Set[NodeType],
+                             hyperparamters_dict, get_data_mappers, algos, node_type: NodeType):
+    """hwer/validation.py:225-240."""
+    results = []
+    recs = []
+    assert len(algos) > 0
+    algos = set(algos)
+    assert len(algos - {"content", "gcn_ncf"}) == 0
+    for algo in algos:
+        hyperparameters = hyperparamters_dict[algo]
+        rec, res, _, _ = test_algorithm(train_affinities, validation_affinities, nodes, node_types, hyperparameters,
+                                        get_data_mappers, algo, node_type)
+        results.extend(res)
+        recs.append(rec)
+    return recs, results
+
+
+test_multiple_algorithms.__test__ = False
+
+
+def display_results(results: List[Dict[str, Any]]):
+    """hwer/validation.py:243-255."""
+    import pandas as pd
+    from tabulate import tabulate
+    df = pd.DataFrame.from_records(results)
+    df = df.groupby(['algo']).mean()
+    df['time'] = df['time'].apply(lambda s: str(datetime.timedelta(seconds=s)))
+    t = df['retrieval_time']
+    df['retrieval_time'] = df['retrieval_time'].apply(lambda s: str(datetime.timedelta(seconds=s)))
+    cols = list(df.columns)
+    for c in [cols[i:i + 8] for i in range(0, len(cols), 8)]:
+        print(tabulate(df[c], headers='keys', tablefmt='psql'))
+    df['retrieval_time'] = t
+    return df
+
+
+def run_model_for_hpo(nodes: List[Node], edges: List[Tuple[Edge, bool]], node_types: Set[NodeType],
+                      retrieved_node_type: NodeType, prepare_data_mappers, hyperparameters, algo):
+    """hwer/validation.py:278-287."""
+    ndcg, ncf_ndcg = run_models_for_testing(nodes, edges, node_types, retrieved_node_type, prepare_data_mappers,
+                                            [algo], {algo: hyperparameters}, display=False)
+    return ndcg, ncf_ndcg
+
+
+def run_models_for_testing(nodes: List[Node], edges: List[Tuple[Edge, bool]], node_types: Set[NodeType],
+                           retrieved_node_type: NodeType, prepare_data_mappers, algos, hyperparamters_dict,
+                           display=True, results_csv="overall_results.csv"):
+    """hwer/validation.py:290-309: edges are (Edge, is_validation) pairs; returns (ndcg_b@100, ncf_ndcg)."""
+    import pandas as pd
+    train_affinities = [e for e, t in edges if not t]
+    validation_affinities = [e for e, t in edges if t]
+    recs, results = test_multiple_algorithms(train_affinities, validation_affinities, nodes, node_types,
+                                             hyperparamters_dict, prepare_data_mappers, algos, retrieved_node_type)
+    ndcg, ncf_ndcg = results[0]['ndcg_b@100'], results[0]['ncf_ndcg']
+    if display:
+        results = display_results(results)
+        if results_csv:
+            results.to_csv(results_csv)
+    else:
+        results = pd.DataFrame.from_records(results)
+        results = results.groupby(["algo"]).mean().reset_index()
+        ndcg, ncf_ndcg = results["ndcg_b@100"].values[0], results["ncf_ndcg"].values[0]
+    return ndcg, ncf_ndcg

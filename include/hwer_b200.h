@@ -187,6 +187,17 @@ int hwer_eval_metrics(const int64_t* topk_dev, int32_t U, int32_t kret, const in
                       const float* val_rel_dev, const int32_t* cutoffs_dev, int32_t n_cut, int64_t n_items,
                       double* out_dev, double* per_user_dev, void* stream);
 
+/* Link-prediction metrics of P scored pairs with 0/1 labels.
+ * Replaces: the sklearn calls of validation.link_prediction_accuracy, hwer/validation.py:52-59 --
+ *           average_precision_score(labels, scores), precision_recall_fscore_support(labels, scores >= 0.5,
+ *           average='binary') and accuracy_score(labels, scores >= 0.5).
+ * scores_dev [P] fp32 (hwer_pair_score / hwer_ncf_score output), labels_dev [P] u8.  out8_dev receives 8 doubles:
+ *   average precision (step-wise over distinct scores, as sklearn), precision, recall, accuracy at
+ *   `threshold` (score >= threshold is a predicted link; undefined ratios are 0 like sklearn's zero_division),
+ *   then the confusion counts tp, fp, fn, tn.  0 < P < 2^31 - 1. */
+int hwer_link_metrics(const float* scores_dev, const uint8_t* labels_dev, int64_t P, float threshold, double* out8_dev,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

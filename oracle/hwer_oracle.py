@@ -337,3 +337,50 @@ def extraction_metrics(predictions, train_edges, validation_edges, node_type, cu
         seen.update(p[:top])
     out["diversity"] = len(seen) / max(len(all_items), 1)          # :144-145
     return out
+
+
+def average_precision_score(labels, scores):
+    """sklearn.metrics.average_precision_score for binary labels (the call at hwer/validation.py:52-53; sklearn is a
+    third-party dependency outside /root/reference, pinned scikit-learn==0.21.3): AP = sum_n (R_n - R_{n-1}) P_n over
+    the DISTINCT score thresholds, scores sorted descending.  Restated with numpy, float64."""
+    labels = np.asarray(labels).astype(np.float64)
+    scores = np.asarray(scores)
+    order = np.argsort(-scores, kind="mergesort")
+    s, y = scores[order], labels[order]
+    ends = np.r_[np.where(np.diff(s))[0], len(s) - 1]             # last index of each group of equal scores
+    tps = np.cumsum(y)[ends]
+    precision = tps / (ends + 1.0)
+    recall = tps / tps[-1]
+    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+
+def link_prediction_metrics(labels, predictions, threshold=0.5):
+    """The metric half of hwer/validation.py:52-64: AP plus precision / recall (average='binary') and accuracy of
+    `predictions >= 0.5`.  Returns (ap, precision, recall, accuracy)."""
+    labels = np.asarray(labels).astype(bool)
+    pred = np.asarray(predictions) >= threshold
+    tp = float(np.sum(labels & pred)); fp = float(np.sum(~labels & pred))
+    fn = float(np.sum(labels & ~pred)); tn = float(np.sum(~labels & ~pred))
+    precision = tp / (tp + fp) if tp + fp > 0 else 0.0
+    rec = tp / (tp + fn) if tp + fn > 0 else 0.0
+    return average_precision_score(labels, predictions), precision, rec, (tp + tn) / max(len(labels), 1)
+
+
+def link_prediction_accuracy(model, nodes, train_edges, validation_edges, rng):
+    """hwer/validation.py:41-65.  `rng` is the `random` module (or a random.Random): the reference draws
+    10 x |E| negative pairs with random.choices in this exact order -- train src, train dst, validation src,
+    validation dst -- so a seeded generator reproduces its pair sets."""
+    m = 10
+    out = {}
+    sets = {}
+    for name, edges in (("train", train_edges), ("val", validation_edges)):
+        neg_src = rng.choices(nodes, k=len(edges) * m)
+        neg_dst = rng.choices(nodes, k=len(edges) * m)
+        sets[name] = ([(u, i) for u, i, r in edges] + list(zip(neg_src, neg_dst)),
+                      [1] * len(edges) + [0] * (len(edges) * m))
+    for name in ("train", "val"):                                  # predictions after BOTH sets are drawn (:44-51)
+        pairs, labels = sets[name]
+        ap, p, r, a = link_prediction_metrics(labels, np.array(model.predict(pairs)))
+        out["lp_%s_ap" % name], out["lp_%s_precision" % name] = ap, p
+        out["lp_%s_recall" % name], out["lp_%s_accuracy" % name] = r, a
+    return out

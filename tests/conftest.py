@@ -66,3 +66,8 @@ def synthetic_edges(n_users, n_items, seed, val_per_user=3, min_train=5, max_tra
             if u % 5 == 0:
                 val.append((u, int(items[0]), 5.0))
     return train, val
+
+
+@pytest.fixture(scope="session")
+def golden_lp():
+    return np.load(os.path.join(GOLDEN, "reference_lp.npz"))

@@ -404,7 +404,7 @@ class _Exchange:
 # (one GPU plays every rank here, so batches stay small: a rank's waiting kernels must leave SMs free for the kernels
 #  of the ranks it waits for -- with one GPU per rank, as deployed, that coupling does not exist)
 @pytest.mark.parametrize("world,B,k,share", [(2, 50, 100, 1), (3, 7, 10, 1), (1, 33, 20, 1), (3, 40, 100, 1),
-                                             (2, 50, 100, 0), (3, 9, 10, 0)])
+                                             (2, 50, 100, 0), (3, 9, 10, 0), (2, 12, 1000, 1)])
 def test_peer_exchange_protocol_on_one_gpu(hw, world, B, k, share):
     """hwer_topk_sharded with `world` ranks living in ONE process: one exchange buffer, index (a row shard) and
     stream per rank.  Exercises the real protocol -- per-round threshold sharing (share=1), final kernel storing

@@ -174,3 +174,40 @@ def test_ncf_predict_indexing_matches_reference(golden_ncf):
     g = golden_ncf
     got = O.ncf_forward(g["h"], g["predict_src"] + 1, g["predict_dst"] + 1, g["params_d3"], 3)
     np.testing.assert_allclose(got, g["predict"], rtol=0, atol=2e-6)
+
+
+# ----------------------------------------------------------------------------- link prediction (validation.py:41-65)
+def _eval_case(golden):
+    nu, ni, dd = [int(x) for x in golden["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, seed=int(golden["seeds"][0]))
+    users = [O.Node("user", i) for i in range(nu)]
+    items = [O.Node("item", i) for i in range(ni)]
+    m = O.OracleRecommender({"user", "item"}, n_dims=dd)
+    m.add_nodes(users + items)
+    m.build_knn(O.unit_length(collab, axis=1))
+    tr, vl = synthetic_edges(nu, ni, seed=int(golden["seeds"][1]))
+    return m, users + items, [(users[u], items[i], w) for u, i, w in tr], [(users[u], items[i], w) for u, i, w in vl]
+
+
+def test_link_prediction_accuracy_matches_reference(golden_lp):
+    import random
+    m, nodes, train, val = _eval_case(golden_lp)
+    keys = [str(k) for k in golden_lp["lp_keys"]]
+    random.seed(int(golden_lp["seeds"][2]))
+    got = O.link_prediction_accuracy(m, nodes, train, val, random)
+    for k, v in zip(keys, golden_lp["lp_values"]):
+        assert abs(got[k] - v) < 1e-12, (k, got[k], v)
+    random.seed(int(golden_lp["seeds"][3]))
+    got = O.link_prediction_accuracy(m, nodes, train[:500], val[:50], random)
+    for k, v in zip(keys, golden_lp["lp2_values"]):
+        assert abs(got[k] - v) < 1e-12, (k, got[k], v)
+
+
+def test_average_precision_restatement_equals_sklearn_with_ties():
+    from sklearn.metrics import average_precision_score
+    rs = np.random.RandomState(3)
+    for n, levels in ((1000, 7), (5000, 100000), (10, 2), (257, 1)):
+        y = rs.randint(0, 2, n)
+        y[0] = 1
+        s = rs.randint(0, levels, n).astype(np.float32) / levels
+        assert abs(O.average_precision_score(y, s) - average_precision_score(y, s)) < 1e-12
