@@ -4,6 +4,10 @@ reference is single-process).
 GPU g owns the contiguous catalogue rows [g*N/G, (g+1)*N/G); queries are replicated; every rank computes its
 local exact top-k (rows offset to global ids, fp64 scores), one all-gather exchanges the [B, k] results, and the
 merge kernel applies the same (score desc, row asc) rule -- so 1, 2, 4 and 8-GPU runs return identical results.
+
+Small catalogues served to ALL users (configs C2 / C3: the item table is <= 28 MB) shard the other way:
+`QueryShardedTopK` replicates the table, gives every rank a contiguous slice of the queries and needs no
+collective on the data path -- only an optional all-gather of the finished [B, k] results.
 """
 import ctypes
 from typing import Tuple
@@ -180,3 +184,48 @@ class ShardedTopK:
         if self._px is not None:
             self._px.close()
             self._px = None
+
+
+# --------------------------------------------------------------------------- query sharding (replicated catalogue)
+def gather_query_shards(idx, score, n_queries: int, group=None):
+    """All-gather of per-rank result slices ([B_r, k] rows + scores, B_r = partition(n_queries, G, r)) into the
+    full [n_queries, k] arrays, in query order, on every rank.  One collective: slices are padded to the largest."""
+    world = dist.get_world_size(group)
+    k = idx.shape[1]
+    rows_max = max(partition(n_queries, world, r)[1] - partition(n_queries, world, r)[0] for r in range(world))
+    packed = torch.zeros((2, rows_max, k), dtype=torch.int64, device=idx.device)
+    packed[0, :idx.shape[0]] = idx
+    packed[1, :idx.shape[0]] = score.double().view(torch.int64)
+    out = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(out, packed, group=group)
+    idx_parts, sc_parts = [], []
+    for r in range(world):
+        b, e = partition(n_queries, world, r)
+        idx_parts.append(out[r][0, :e - b])
+        sc_parts.append(out[r][1, :e - b].contiguous().view(torch.float64))
+    return torch.cat(idx_parts, dim=0), torch.cat(sc_parts, dim=0).to(score.dtype)
+
+
+class QueryShardedTopK:
+    """All-users retrieval over a catalogue that every GPU holds in full: rank r answers queries
+    [r*B/G, (r+1)*B/G).  Results are bit-identical to one GPU answering all B (each query's search is independent
+    of the others)."""
+
+    def __init__(self, table, shadow=None, group=None, max_norm=None):
+        self.group = group
+        self.index = ops.TopKIndex(table, shadow, max_norm=max_norm)
+
+    def local_slice(self, n_queries: int) -> Tuple[int, int]:
+        if not dist.is_initialized():
+            return 0, n_queries
+        return partition(n_queries, dist.get_world_size(self.group), dist.get_rank(self.group))
+
+    def topk(self, queries, k, mode="exact", gather=True):
+        """queries: the FULL [B, d] batch (replicated, e.g. all user rows).  Returns this rank's slice when
+        gather=False, else the full [B, k] result on every rank."""
+        B = queries.shape[0]
+        b, e = self.local_slice(B)
+        idx, score = self.index.topk(queries[b:e].contiguous(), int(k), mode)[:2]
+        if not gather or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return idx, score
+        return gather_query_shards(idx, score, B, self.group)

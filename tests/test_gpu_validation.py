@@ -179,3 +179,64 @@ def test_topk_1000_matches_oracle(hw, n, d, B, k):
                                       torch.stack([p[0] for p in parts]).contiguous(), want_f64=True)
     np.testing.assert_array_equal(midx.cpu().numpy(), idx)
     np.testing.assert_array_equal(ms64.cpu().numpy(), s64)
+
+
+def test_query_sharded_single_process_equals_plain_index(hw):
+    rs = np.random.RandomState(4)
+    t = torch.from_numpy(O.unit_length(rs.standard_normal((27278, 256)).astype(np.float32), axis=1)).cuda()   # C3 items
+    q = torch.from_numpy(O.unit_length(rs.standard_normal((700, 256)).astype(np.float32), axis=1)).cuda()
+    a = hw.sharded.QueryShardedTopK(t).topk(q, 100)
+    b = hw.ops.TopKIndex(t).topk(q, 100)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert hw.sharded.QueryShardedTopK(t).local_slice(700) == (0, 700)
+
+
+def test_c5_shard_properties_62m_top1000(hw):
+    """Config C5 as one of its eight GPUs sees it: a 62.5 M x 128 shard (32 GB fp32 + 16 GB bf16 shadow), exact
+    top-1000, batch 4096, rows offset to the shard's global ids.  Size-independent properties only."""
+    n, d, k, B, shard = 62_500_000, 128, 1000, 4096, 7
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90 * (1 << 30):
+        pytest.skip("needs ~60 GB of free HBM")
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    table = torch.empty((n, d), dtype=torch.float32, device="cuda")
+    step = 4_000_000
+    for b in range(0, n, step):
+        e = min(n, b + step)
+        table[b:e] = hw.ops.unit_length(torch.randn((e - b, d), generator=gen, device="cuda"))
+    q = hw.ops.unit_length(torch.randn((B, d), generator=gen, device="cuda"))
+    for j in range(3):                                   # plant exact copies: first tile, middle, the very last row
+        table[(5, n // 2 + 11, n - 1)[j]] = q[j]
+    shadow = hw.ops.make_shadow(table)
+    v_, _, _, _, mx = hw.ops.norm_stats(table)
+    assert v_ == 0
+    index = hw.ops.TopKIndex(table, shadow, max_norm=mx)
+    off = shard * n
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    index.topk(q[:256].contiguous(), k, idx_offset=off)  # sizes the workspace
+    t0.record()
+    idx, sc, s64 = index.topk(q, k, idx_offset=off, want_f64=True)
+    t1.record()
+    torch.cuda.synchronize()
+    print("C5 shard: %d x %d, top-%d, batch %d: %.1f ms" % (n, d, k, B, t0.elapsed_time(t1)))
+    assert bool((s64[:, :-1] >= s64[:, 1:]).all())                                   # sortedness
+    assert int(idx.min().item()) >= off and int(idx.max().item()) < off + n          # global ids of this shard
+    srt = idx.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                                   # no duplicates in any row
+    for j in range(3):
+        assert idx[j, 0].item() == off + (5, n // 2 + 11, n - 1)[j] and abs(s64[j, 0].item() - 1.0) < 1e-6
+    # returned scores are the fp64 dot products of the returned rows
+    sub = slice(0, 64)
+    rows = table[(idx[sub] - off).reshape(-1)].double().reshape(64, k, d)
+    np.testing.assert_allclose(torch.einsum("bkd,bd->bk", rows, q[sub].double()).cpu().numpy(),
+                               s64[sub].cpu().numpy(), atol=1e-12)
+    # nothing outside the result beats its k-th score: independent fp64 pass over the whole shard
+    for j in (0, 1000, 4095):
+        full = torch.cat([table[b:b + step].double() @ q[j].double() for b in range(0, n, step)])
+        kth = s64[j, -1].item()
+        assert int((full > kth + 1e-12).sum().item()) <= k - 1 and int((full >= kth - 1e-12).sum().item()) >= k
+        assert set(torch.topk(full, k).indices.cpu().tolist()) == set((idx[j] - off).cpu().tolist())
+        del full
+    # batch independence: a query answered alone gives the same row
+    i1, _, s1 = index.topk(q[1000:1001].contiguous(), k, idx_offset=off, want_f64=True)
+    assert torch.equal(i1[0], idx[1000]) and torch.equal(s1[0], s64[1000])

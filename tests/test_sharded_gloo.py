@@ -61,3 +61,33 @@ def test_small_shard_is_padded():
     s = torch.rand(2, 3, dtype=torch.float64)
     pi, ps = pad_local_result(idx, s, 5)
     assert pi.shape == (2, 5) and torch.all(pi[:, 3:] == -1) and torch.all(torch.isinf(ps[:, 3:]))
+
+
+def _query_worker(rank, world, port, n, d, B, k, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hwer_oracle as O
+    from hwer_b200.sharded import gather_query_shards, partition
+    rs = np.random.RandomState(6)
+    table = O.unit_length(rs.standard_normal((n, d)).astype(np.float32), axis=1)
+    q = O.unit_length(rs.standard_normal((B, d)).astype(np.float32), axis=1)
+    b, e = partition(B, world, rank)
+    idx, sc = O.exact_topk(table, q[b:e], k)        # the oracle plays this rank's search over the replicated table
+    gi, gs = gather_query_shards(torch.from_numpy(idx), torch.from_numpy(sc.astype(np.float32)), B)
+    assert gi.shape == (B, k) and gs.shape == (B, k) and gs.dtype == torch.float32
+    ref_idx, ref_sc = O.exact_topk(table, q, k)
+    np.testing.assert_array_equal(gi.numpy(), ref_idx)
+    np.testing.assert_array_equal(gs.numpy(), ref_sc.astype(np.float32))
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_query_sharding_gathers_in_query_order(tmp_path):
+    n, d, B, k = 500, 16, 11, 7                     # 11 queries over 2 ranks: unequal slices (5 and 6)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_query_worker, args=(2, port, n, d, B, k, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok0")) and os.path.exists(os.path.join(str(tmp_path), "ok1"))
