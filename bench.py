@@ -344,6 +344,35 @@ def run_b200(a):
         return dict({"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                      "basis": pk["basis"] + " (copy bandwidth)"}, **extra)
 
+    # ---- multi-GPU preflight: the peer-memory exchange must reproduce the NCCL all-gather + merge answer bit for
+    # bit before it is timed; if a peer fails to show up (HWER_E_PEER) or the answers differ, every rank switches to
+    # the NCCL exchange together and the JSON line says so (the number is then the plain path's, not a crash)
+    exchange_note = None
+    if world > 1 and a.exchange == "p2p":
+        qp = queries_for(a.batch)
+        ok, why = 1, ""
+        try:
+            idx_p, sc_p = shard.topk(qp, a.k, a.mode)
+        except _native.HwerError as ex:
+            ok, why = 0, str(ex)
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        plain = hw.sharded.ShardedTopK(table, begin, shadow=shadow, max_norm=max_norm, exchange="nccl")
+        if int(agree.item()) == 1:
+            idx_n, sc_n = plain.topk(qp, a.k, a.mode)
+            same = int(torch.equal(idx_p, idx_n) and torch.equal(sc_p, sc_n))
+            agree = torch.tensor([same], dtype=torch.int32, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            why = why or "peer exchange and NCCL exchange disagreed in the preflight step"
+        if int(agree.item()) == 0:
+            exchange_note = "fell back to the NCCL exchange: %s" % (why or "a peer rank reported a failure")
+            a.exchange = "nccl"
+            shard.close()
+            shard, index = plain, plain.index
+        else:
+            plain.close()
+            del plain
+
     # ---- headline: device-resident throughput (events on the launching stream), clocks sampled meanwhile
     sampler = ClockSampler(local) if rank == 0 else None
     ms, _, _, _, out = measure(a.batch, a.steps, a.warmup, profile=False)
@@ -418,6 +447,8 @@ def run_b200(a):
                                 "frac": blend_bytes / (blend_ms * 1e-3) / 1e9 / pk["hbm"], "bound": "hbm"},
             "result_checksum": int(idx_chk.sum().item()),
         }
+        if exchange_note:
+            line["config"]["exchange_note"] = exchange_note
         print(json.dumps(line), flush=True)
     if world > 1:
         if shard._px is not None:
