@@ -37,6 +37,7 @@ SIGNATURES = {
     "hwer_topk_finish": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
     "hwer_profile": (c_int, [c_void_p, c_int]),
     "hwer_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
+    "hwer_profile_launches": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int32, POINTER(c_int32)]),
     "hwer_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "hwer_merge_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hwer_exchange_bytes": (c_int64, [c_int32, c_int32, c_int32]),
@@ -71,7 +72,7 @@ class HwerError(RuntimeError):
 
 
 def library_path():
-    return _build.LIB
+    return os.environ.get("HWER_B200_LIB") or _build.LIB
 
 
 def lib():
@@ -79,8 +80,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.is_stale():
+    path = os.environ.get("HWER_B200_LIB") or _build.LIB      # override: A/B runs of two builds (scripts/ab_rounds.py)
+    if path == _build.LIB and _build.is_stale():
         try:
             _build.build()
         except Exception as e:

@@ -74,6 +74,9 @@ struct hwer_index {
     float* margin = nullptr;
     float* floor = nullptr;
     size_t ws_queries = 0, ws_cap = 0;
+    uint4* spill = nullptr;                // hit entries of the filter rounds (FilterParams::spill)
+    unsigned int* spill_cnt = nullptr;
+    int spill_cap = 0;
     unsigned int* needed_dev = nullptr;
     unsigned int* needed_host = nullptr;   // pinned
     unsigned int last_cap = 0;
@@ -109,6 +112,27 @@ int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
     }
     ix->ws_queries = q;
     ix->ws_cap = c;
+    return HWER_OK;
+}
+
+// Per-thread spill buffers of the tensor-core filter: sized for twice the hits a thread expects in one round
+// (~1.4 k g candidates per query and round, spread over every epilogue thread of the grid), 16..128 entries.
+int ensure_spill(hwer_index* ix, int Bc, int k, int growth) {
+    if (!ix->use_tc) return HWER_OK;
+    const double per_thread = 1.4 * k * growth * (double)Bc / (double)hwer::filter_tc_spill_buffers(ix->num_sms);
+    int want = 16;
+    while (want < 2.0 * per_thread + 8.0 && want < 128) want <<= 1;
+    if (want <= ix->spill_cap) return HWER_OK;
+    HWER_CUDA(cudaDeviceSynchronize());
+    if (ix->spill) cudaFree(ix->spill);
+    if (ix->spill_cnt) cudaFree(ix->spill_cnt);
+    ix->spill = nullptr; ix->spill_cnt = nullptr; ix->spill_cap = 0;
+    if (cudaMalloc(&ix->spill, hwer::filter_tc_spill_entries(ix->num_sms, want) * 48) != cudaSuccess ||
+        cudaMalloc(&ix->spill_cnt, hwer::filter_tc_spill_buffers(ix->num_sms) * sizeof(unsigned int)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HWER_E_NOMEM, "hwer_topk: cannot allocate the spill buffers");
+    }
+    ix->spill_cap = want;
     return HWER_OK;
 }
 
@@ -260,6 +284,8 @@ int hwer_index_destroy(hwer_index_t* ix) {
     if (ix->thr) cudaFree(ix->thr);
     if (ix->margin) cudaFree(ix->margin);
     if (ix->floor) cudaFree(ix->floor);
+    if (ix->spill) cudaFree(ix->spill);
+    if (ix->spill_cnt) cudaFree(ix->spill_cnt);
     if (ix->needed_dev) cudaFree(ix->needed_dev);
     if (ix->needed_host) cudaFreeHost(ix->needed_host);
     for (auto& e : ix->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -295,6 +321,8 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
     if (chunk < 256) chunk = 256;
     if (chunk > (size_t)B) chunk = B;
     rc = ensure_workspace(ix, chunk, sch.cap);
+    if (rc) return rc;
+    rc = ensure_spill(ix, (int)chunk, k, sch.growth);
     if (rc) return rc;
     ix->last_cap = sch.cap;
 
@@ -343,7 +371,9 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 p.n_items = ix->n; p.tile_begin = (int)seen_l; p.tile_end = (int)end;
                 p.tile_mul = ix->tile_mul; p.tile_mod = T;
                 p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics
+                p.spill = ix->spill; p.spill_cnt = ix->spill_cnt; p.spill_cap = ix->spill_cap; p.spill_ctas = ix->num_sms;
                 HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
+                if (round > 0) ix->other_launches += 1;     // spill_extract_kernel rides behind every filter round
             } else {
                 long long rb = seen_l * hwer::kTileItems, re = end * hwer::kTileItems;
                 if (re > ix->n) re = ix->n;
@@ -600,6 +630,19 @@ int hwer_profile_read(hwer_index_t* ix, void* stream_v, double* filter_ms, int64
     if (other_launches) *other_launches = ix->other_launches;
     ix->ev_used = 0;
     ix->filter_launches = ix->other_launches = 0;
+    return HWER_OK;
+}
+
+int hwer_profile_launches(hwer_index_t* ix, void* stream_v, double* out_ms, int32_t cap, int32_t* n_out) {
+    if (!ix || !n_out || cap < 0 || (cap > 0 && !out_ms)) return fail(HWER_E_INVALID, "hwer_profile_launches: bad argument");
+    HWER_CUDA(cudaSetDevice(ix->device));
+    HWER_CUDA(cudaStreamSynchronize((cudaStream_t)stream_v));
+    *n_out = (int32_t)ix->ev_used;
+    for (size_t i = 0; i < ix->ev_used && i < (size_t)cap; ++i) {
+        float t = 0.f;
+        HWER_CUDA(cudaEventElapsedTime(&t, ix->ev[i].first, ix->ev[i].second));
+        out_ms[i] = t;
+    }
     return HWER_OK;
 }
 

@@ -45,12 +45,18 @@ struct FilterParams {
     int tmem_cols;            // power of two >= acc_stages * nq
     int stream_once;          // 1: item tiles are read by one CTA only -> L2 evict-first
     int dense;                // 1: round 0, every score is written at its position in the round (no atomics)
+    uint4* spill;             // [spill_ctas * 512 threads][spill_cap][3] hit entries of the filter rounds (48 B each)
+    unsigned int* spill_cnt;  // [spill_ctas * 512] entries written by each epilogue thread of the last launch
+    int spill_cap;            // entries per thread
+    int spill_ctas;           // CTAs the spill buffers were sized for (>= grid)
     float* dump;              // debug: full score matrix [n_items, dump_ld] (nullptr in production)
     long long dump_ld;
 };
 
 cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sms, cudaStream_t stream);
 size_t filter_tc_smem_bytes(int nq, int kb, int stages);
+size_t filter_tc_spill_entries(int num_sms, int spill_cap);   // 48-byte entries to allocate for FilterParams::spill
+size_t filter_tc_spill_buffers(int num_sms);                  // counters to allocate for FilterParams::spill_cnt
 int filter_tc_pick_stages(int nq, int kb);
 
 // Generic CUDA-core variant for widths the tensor-core tile does not cover (d_pad > 256).

@@ -15,6 +15,8 @@
 //   UMMA K = 16, d_pad/16 steps  (accumulators: fp32 in TMEM, acc_stages-deep)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
 // warps 2..17 = epilogue (tcgen05.ld -> release the accumulator -> sign test of score - thr -> rare append).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,7 +28,6 @@ constexpr int kSlabBytes = kTileItems * 128;  // one 64-wide K block of an item 
 constexpr int kEpiWarps = 16;                 // four per TMEM lane quadrant (one SM scheduler each), splitting the
                                               // query columns: the epilogue is latency-, not issue-bound
 constexpr int kThreadsTc = (2 + kEpiWarps) * 32;
-constexpr int kHitQueue = 64;                 // per-warp shared-memory hit queue (entries)
 constexpr int kColParts = kEpiWarps / 4;      // warps sharing a lane quadrant
 constexpr int kBiasRowBytes = 32;             // K=16 bf16 per row of the threshold-MMA operands
 
@@ -38,47 +39,52 @@ __device__ __forceinline__ void append_candidate(unsigned long long* cand, unsig
     if (slot < cap) cand[(size_t)q * cap + slot] = make_key(s, row);
 }
 
-// Per-warp hit queue in shared memory.  Hits are rare (DESIGN.md "hit rate"): a lane that finds one parks it here
-// with a shared-memory atomic; the global atomicAdd that allocates the slot in the query's candidate list is
-// issued by the whole warp at the start of the NEXT tile and its result consumed at that tile's end, so the ~1 us
-// L2 round trip overlaps a tile of work instead of stalling the warp.
-struct HitCtx {
-    uint32_t slots;               // shared-space address of [kHitQueue] x {key lo, key hi, query, -}
-    uint32_t count;               // shared-space address of the number of entries parked since the last drain
-                                  // (may exceed kHitQueue: the overflow was appended directly)
+// Hits leave the kernel as SPILL ENTRIES.  With two accumulator stages the slowest of a tile's 16 epilogue warps sets
+// the pace of the tensor pipe, so what matters is the latency a hit adds inside a warp.  Walking a row's values,
+// allocating a slot in the query's candidate list (a global atomic) and writing the key cost 300-400 cycles per hit
+// however the appends were queued or deferred (v9-v12: the five hit-heavy rounds of a B = 4096 step took 2.3 ms for
+// 0.7 ms of MMA work, profiles/README.md).  Instead, a lane that sees a non-negative (score - thr) in a group of 8
+// columns stores the group's 8 raw values plus (row, first query of the group) -- 48 bytes, three fire-and-forget
+// 128-bit stores -- into its thread's PRIVATE append buffer in global memory: no atomic, no shared counter, no
+// branch per column, nothing to wait for.  spill_extract_kernel, launched right behind the filter kernel, walks
+// the entries with one thread each and does the per-hit work at full memory-level parallelism.
+// A thread whose buffer is full (heavily tied data) falls back to the blocking append below.
+struct SpillCtx {
+    uint4* mine;                  // this thread's buffer [spill_cap][3]
+    uint32_t n;                   // entries written (may exceed spill_cap: the excess was appended directly)
 };
 
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
+// What the threshold MMA subtracts for a query: thr ~ hi + lo with both parts bf16 and hi + lo <= thr (lo rounds
+// toward -inf), so folding it into the MMA only ever admits more; "no threshold yet" (-inf) becomes the query's
+// floor.  Returns hi + lo and the two negated bf16 bit patterns of the bias operand.
+__device__ __forceinline__ float thr_split(float t, uint32_t& nhi, uint32_t& nlo) {
+    t = fminf(t, 3.0e38f);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+    const float rem = t - __bfloat162float(hi);
+    const uint32_t u = __float_as_uint(rem);
+    uint32_t lo_bits = u & 0xFFFF0000u;
+    if ((u & 0x80000000u) && (u & 0xFFFFu)) lo_bits += 0x10000u;     // negative: away from zero
+    nhi = (uint32_t)(__bfloat16_as_ushort(hi) ^ 0x8000u);
+    nlo = (lo_bits >> 16) ^ 0x8000u;
+    return __bfloat162float(hi) + __uint_as_float(lo_bits);
 }
 
-// Out of line on purpose: 64 call sites per epilogue warp, executed by the odd lane only.  Everything is passed in
-// registers and the queue is addressed in the shared window (ATOMS/STS, not generic atomics).
-__device__ __noinline__ void push_hit(uint32_t slots, uint32_t count, const FilterParams* p, float score,
-                                      uint32_t row, int q) {
-    uint32_t s;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(s) : "r"(count) : "memory");
-    const unsigned long long k = make_key(score, row);
-    if (s < (uint32_t)kHitQueue) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slots + s * 16u), "r"((uint32_t)k),
-                     "r"((uint32_t)(k >> 32)), "r"((uint32_t)q), "r"(0u)
-                     : "memory");
-    } else {                        // queue full (only the hit-dense first rounds): append directly
-        const unsigned int slot = atomicAdd(&p->cnt[q], 1u);
-        if (slot < p->cap) p->cand[(size_t)q * p->cap + slot] = k;
-    }
+__device__ __forceinline__ float query_threshold(const FilterParams& p, int q) {
+    return q < p.B ? fmaxf(p.thr[q], p.floor[q]) : __int_as_float(0x7f800000);   // padded query: never admits
 }
 
-// Blocking drain of queue entries [begin, end) by the whole warp.
-__device__ __noinline__ void hit_queue_flush(uint32_t slots, const FilterParams* p, int begin, int end) {
-    const int lane = threadIdx.x & 31;
-    for (int base = begin; base < end; base += 32) {
-        if (base + lane < end) {
-            const uint4 e = lds_v4(slots + (uint32_t)(base + lane) * 16u);
-            const unsigned int slot = atomicAdd(&p->cnt[e.z], 1u);
-            if (slot < p->cap) p->cand[(size_t)e.z * p->cap + slot] = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+// Buffer full: blocking append of the hits of one 8-column group.  Out of line, rarely taken.
+__device__ __noinline__ void append_group_direct(const FilterParams* p, uint4 a, uint4 b, uint32_t thr_addr,
+                                                 uint32_t row, int q0) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const float diff = __uint_as_float(w[j]);
+        if (diff >= 0.0f) {
+            float thr;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(thr_addr + (uint32_t)j * 4u));
+            const unsigned int slot = atomicAdd(&p->cnt[q0 + j], 1u);
+            if (slot < p->cap) p->cand[(size_t)(q0 + j) * p->cap + slot] = make_key(diff + thr, row);
         }
     }
 }
@@ -94,7 +100,7 @@ __device__ __forceinline__ uint32_t and8(const uint32_t* v) {
 // against the 32 queries they belong to.
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* thr_s, int c0, int q_base,
-                                               uint32_t row, bool row_ok, const FilterParams& p, const HitCtx& h,
+                                               uint32_t row, bool row_ok, const FilterParams& p, SpillCtx& sp,
                                                uint32_t dense_pos) {
     if (MODE == kModeDump) {
         if (row_ok) {
@@ -125,14 +131,101 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if ((int)grp[g] >= 0) {
+                const uint4 a = make_uint4(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3]);
+                const uint4 b = make_uint4(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]);
+                if (sp.n < (uint32_t)p.spill_cap) {
+                    uint4* e = sp.mine + (size_t)sp.n * 3;
+                    e[0] = a;
+                    e[1] = b;
+                    e[2] = make_uint4(row, (uint32_t)(q_base + c0 + 8 * g), 0u, 0u);
+                } else {
+                    append_group_direct(&p, a, b, smem_u32(thr_s + c0 + 8 * g), row, q_base + c0 + 8 * g);
+                }
+                ++sp.n;
+            }
+        }
+    }
+}
+
+// The per-hit work the filter kernel's epilogue does not do.  Block b owns the 512 spill buffers of filter CTA b,
+// one thread per buffer.  All of a filter CTA's hits belong to the (usually one) query block it scored, so the
+// block first COUNTS its hits per query in shared memory, reserves one contiguous range per query in the global
+// candidate lists with a single atomicAdd, and then walks the entries again to write the keys: ~30x fewer global
+// atomics than one per hit at B = 4096, and at small batches (all hits on a few dozen counters) the per-address
+// serialisation in L2 that bounded the early rounds is gone.
+__device__ __forceinline__ void load_entry(const uint4* e, uint4& a, uint4& b) {
+    a = e[0];
+    b = e[1];
+}
+
+constexpr int kExtractSub = 2;                                  // threads sharing one buffer (entries interleaved)
+constexpr int kExtractThreads = kEpiWarps * 32 * kExtractSub;
+
+__global__ void __launch_bounds__(kExtractThreads)
+spill_extract_kernel(const __grid_constant__ FilterParams p) {
+    __shared__ unsigned int cnt_s[kMaxNQ];      // hits per query of the block, then the write cursor
+    __shared__ float thr_x[kMaxNQ];             // what the threshold MMA subtracted for the query
+    const int tid = threadIdx.x;
+    const size_t buf = (size_t)blockIdx.x * (kEpiWarps * 32) + (tid / kExtractSub);
+    unsigned int n = p.spill_cnt[buf];
+    if (n > (unsigned int)p.spill_cap) n = (unsigned int)p.spill_cap;
+    if (__syncthreads_or(n != 0u) == 0) return;                      // nothing spilled by this filter CTA
+    const uint4* e0 = p.spill + buf * (size_t)p.spill_cap * 3;
+    const int nq = p.nq;
+    unsigned int cursor = (unsigned int)(tid % kExtractSub);         // this thread's entries: cursor, cursor + Sub, ...
+    for (int qb = (int)blockIdx.x / p.slots; qb < p.nqb; qb += p.qb_step) {     // the filter CTA's query blocks
+        const int q_base = qb * nq;
+        for (int i = tid; i < nq; i += kExtractThreads) cnt_s[i] = 0u;
+        __syncthreads();
+        unsigned int end = cursor;
+        {                                                                       // pass 1: count
+            uint4 a, b, m;
+            if (end < n) { const uint4* e = e0 + (size_t)end * 3; a = e[0]; b = e[1]; m = e[2]; }
+            while (end < n) {
+                const int ql = (int)m.y - q_base;
+                if (ql >= nq) break;                                            // a later query block's entry
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                end += kExtractSub;
+                if (end < n) { const uint4* e = e0 + (size_t)end * 3; a = e[0]; b = e[1]; m = e[2]; }   // next in flight
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (__uint_as_float(w[j]) >= 0.0f) atomicAdd(&cnt_s[ql + j], 1u);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nq; i += kExtractThreads) {                       // one global atomic per query
+            const unsigned int c = cnt_s[i];
+            if (c) {
+                uint32_t nhi, nlo;
+                thr_x[i] = thr_split(query_threshold(p, q_base + i), nhi, nlo);
+                cnt_s[i] = atomicAdd(&p.cnt[q_base + i], c);
+            }
+        }
+        __syncthreads();
+        {                                                                       // pass 2: write the keys
+            unsigned int i = cursor;
+            uint4 a, b, m;
+            if (i < end) { const uint4* e = e0 + (size_t)i * 3; a = e[0]; b = e[1]; m = e[2]; }
+            while (i < end) {
+                const int ql = (int)m.y - q_base;
+                const uint32_t row = m.x;
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                i += kExtractSub;
+                if (i < end) { const uint4* e = e0 + (size_t)i * 3; a = e[0]; b = e[1]; m = e[2]; }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float diff = __uint_as_float(v[8 * g + j]);            // score - thr (NaN stays NaN)
-                    // the key carries score = diff + thr: one fp32 rounding (~3e-8), far inside the margin
-                    if (diff >= 0.0f) push_hit(h.slots, h.count, &p, diff + thr_s[c0 + 8 * g + j], row, q_base + c0 + 8 * g + j);
+                    const float diff = __uint_as_float(w[j]);                   // score - thr (NaN stays NaN)
+                    if (diff >= 0.0f) {
+                        const unsigned int pos = atomicAdd(&cnt_s[ql + j], 1u);
+                        // the key carries score = diff + thr: one fp32 rounding (~3e-8), far inside the margin
+                        if (pos < p.cap)
+                            p.cand[(size_t)(q_base + ql + j) * p.cap + pos] = make_key(diff + thr_x[ql + j], row);
+                    }
                 }
             }
         }
+        cursor = end;
+        __syncthreads();
     }
 }
 
@@ -153,14 +246,12 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     uint8_t* ones_smem = item_smem + (size_t)p.stages * stage_bytes;   // [128 rows x K16] constant (1, 1, 0, ...)
     uint8_t* bias_smem = ones_smem + kBiasRowBytes * kTileItems;       // [nq rows x K16] (-thr_hi, -thr_lo, 0, ...)
     float* thr_s = reinterpret_cast<float*>(bias_smem + kBiasRowBytes * kMaxNQ);
-    uint4* hitq_s = reinterpret_cast<uint4*>(thr_s + kMaxNQ);                   // [kEpiWarps][kHitQueue]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(hitq_s + kEpiWarps * kHitQueue);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + kMaxNQ);
     uint64_t* full_bar = bars;                            // [stages]   TMA -> MMA
     uint64_t* empty_bar = bars + p.stages;                // [stages]   MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * p.stages;            // [acc]      MMA -> epilogue
     uint64_t* tempty_bar = tfull_bar + p.acc_stages;      // [acc]      epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + p.acc_stages);
-    unsigned int* hitcnt_s = tmem_slot + 2;               // [kEpiWarps]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -183,7 +274,6 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
-    if (threadIdx.x < kEpiWarps) hitcnt_s[threadIdx.x] = 0u;
     if (MODE == kModeFilter) {
         // constant A operand of the threshold MMA: K-major, no swizzle, 8-row core matrices of 128 B;
         // row r, columns 0..7 live at (r/8)*256 + (r%8)*16, columns 8..15 (all zero) 128 B further
@@ -211,6 +301,12 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     // Ring positions persist across query blocks; every role keeps private copies (so they can live in uniform
     // registers where the role is warp-converged) re-derived from this count at the top of each block.
     uint32_t tiles_done = 0;
+    // this thread's private spill buffer (epilogue threads of the filter rounds)
+    SpillCtx sp;
+    sp.n = 0u;
+    sp.mine = nullptr;
+    if (MODE == kModeFilter && warp >= 2)
+        sp.mine = p.spill + ((size_t)blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64)) * (size_t)p.spill_cap * 3;
 
     for (int qb = qb0; qb < p.nqb; qb += p.qb_step) {
         const int q_base = qb * nq;
@@ -243,20 +339,8 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
                 const int q = q_base + i;
                 if (MODE == kModeFilter) {
-                    // thr ~ hi + lo with both parts bf16 and hi + lo <= thr (lo rounds toward -inf), so folding
-                    // it into the MMA only ever admits more; "no threshold yet" (-inf) becomes the query's floor
-                    float t = __int_as_float(0x7f800000);            // padded query: +huge, never admits
-                    if (q < p.B) t = fmaxf(p.thr[q], p.floor[q]);
-                    t = fminf(t, 3.0e38f);
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(t);
-                    const float rem = t - __bfloat162float(hi);
-                    uint32_t u = __float_as_uint(rem);
-                    uint32_t lo_bits = u & 0xFFFF0000u;
-                    if ((u & 0x80000000u) && (u & 0xFFFFu)) lo_bits += 0x10000u;     // negative: away from zero
-                    const float lo = __uint_as_float(lo_bits);
-                    thr_s[i] = __bfloat162float(hi) + lo;                        // what the MMA subtracts
-                    const uint32_t nhi = (uint32_t)(__bfloat16_as_ushort(hi) ^ 0x8000u);
-                    const uint32_t nlo = (lo_bits >> 16) ^ 0x8000u;
+                    uint32_t nhi, nlo;
+                    thr_s[i] = thr_split(query_threshold(p, q), nhi, nlo);       // what the MMA subtracts
                     uint8_t* dst = bias_smem + (i >> 3) * 256 + (i & 7) * 16;
                     *reinterpret_cast<uint4*>(dst) = make_uint4(nhi | (nlo << 16), 0u, 0u, 0u);
                     *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
@@ -335,10 +419,6 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             const uint32_t quad = (uint32_t)warp & 3u;   // TMEM lane quadrant this warp may read
             const int part = e >> 2;                      // its chunks: columns 32*part and 32*part + 128
             const bool two = 32 * part + 128 < nq;        // warp-uniform
-            HitCtx h;
-            h.slots = smem_u32(hitq_s + e * kHitQueue);
-            h.count = smem_u32(hitcnt_s + e);
-            volatile unsigned int* hit_count = hitcnt_s + e;
             uint32_t acc = tiles_done % (uint32_t)p.acc_stages, acc_phase = (tiles_done / (uint32_t)p.acc_stages) & 1u;
             uint32_t phys = phys0;
             const uint32_t lane_row = quad * 32u + (uint32_t)lane;
@@ -346,28 +426,6 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             const uint32_t tbase = tmem_base + ((quad * 32u) << 16) + 32u * (uint32_t)part;
             const int c0 = 32 * part;
             for (int it = 0; it < my_tiles; ++it) {
-                // deferred appends of the previous tile's hits: issue the slot-allocating atomics now ...
-                int pend = 0;
-                unsigned long long pkey = 0ull;
-                unsigned int pq = 0u, pslot = 0u;
-                if (MODE == kModeFilter) {
-                    __syncwarp();
-                    const unsigned int nh = *hit_count;
-                    if (nh) {
-                        const int m = nh < (unsigned int)kHitQueue ? (int)nh : kHitQueue;
-                        if (m > 32) hit_queue_flush(h.slots, &p, 32, m);
-                        pend = m < 32 ? m : 32;
-                        if (lane < pend) {
-                            const uint4 en = lds_v4(h.slots + (uint32_t)lane * 16u);
-                            pkey = (unsigned long long)en.x | ((unsigned long long)en.y << 32);
-                            pq = en.z;
-                            pslot = atomicAdd(&p.cnt[pq], 1u);
-                        }
-                        __syncwarp();
-                        if (lane == 0) *hit_count = 0u;
-                        __syncwarp();
-                    }
-                }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after_sync();
                 uint32_t v0[32], v1[32];
@@ -384,17 +442,8 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 if (phys >= tile_mod) phys -= tile_mod;
                 const bool row_ok = row < n_items;
                 const uint32_t dense_pos = (uint32_t)(t_first - p.tile_begin + it * p.slots) * (uint32_t)kTileItems + lane_row;
-                epilogue_chunk<MODE>(v0, thr_s, c0, q_base, row, row_ok, p, h, dense_pos);
-                if (two) epilogue_chunk<MODE>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, h, dense_pos);
-                // ... and consume their results only now, a whole tile of work later
-                if (lane < pend && pslot < p.cap) p.cand[(size_t)pq * p.cap + pslot] = pkey;
-            }
-            if (MODE == kModeFilter) {
-                __syncwarp();
-                const unsigned int nh = *hit_count;
-                if (nh) hit_queue_flush(h.slots, &p, 0, nh < (unsigned int)kHitQueue ? (int)nh : kHitQueue);
-                __syncwarp();
-                if (lane == 0) *hit_count = 0u;
+                epilogue_chunk<MODE>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
+                if (two) epilogue_chunk<MODE>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
             }
         }
         tiles_done += (uint32_t)my_tiles;
@@ -402,6 +451,8 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         __syncthreads();
     }
 
+    if (MODE == kModeFilter && warp >= 2)
+        p.spill_cnt[(size_t)blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64)] = sp.n;
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -513,7 +564,7 @@ cudaError_t launch_tc_variant(int mode, int kb, int grid, size_t smem, const CUt
 
 size_t filter_tc_smem_bytes(int nq, int kb, int stages) {
     return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + kMaxNQ * sizeof(float) +
-           (size_t)kBiasRowBytes * (kTileItems + kMaxNQ) + (size_t)kEpiWarps * kHitQueue * sizeof(uint4) +
+           (size_t)kBiasRowBytes * (kTileItems + kMaxNQ) +
            (2 * stages + 8) * sizeof(uint64_t) + 16 + kEpiWarps * sizeof(unsigned int);
 }
 
@@ -548,8 +599,16 @@ cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sm
     p.tile_step = ((long long)p.slots * p.tile_mul) % p.tile_mod;
     const size_t smem = filter_tc_smem_bytes(p.nq, p.kb, p.stages);
     const int mode = p.dump ? kModeDump : (p.dense ? kModeDense : kModeFilter);
-    return launch_tc_variant(mode, p.kb, grid, smem, tmap, p, stream);
+    if (mode == kModeFilter && (!p.spill || !p.spill_cnt || p.spill_cap < 1 || grid > p.spill_ctas))
+        return cudaErrorInvalidValue;
+    cudaError_t e = launch_tc_variant(mode, p.kb, grid, smem, tmap, p, stream);
+    if (e != cudaSuccess || mode != kModeFilter) return e;
+    spill_extract_kernel<<<grid, kExtractThreads, 0, stream>>>(p);
+    return cudaGetLastError();
 }
+
+size_t filter_tc_spill_entries(int num_sms, int spill_cap) { return (size_t)num_sms * kEpiWarps * 32 * spill_cap; }
+size_t filter_tc_spill_buffers(int num_sms) { return (size_t)num_sms * kEpiWarps * 32; }
 
 cudaError_t launch_filter_simt(const float* table, long long n_items, int d, const float* queries, int B,
                                const float* thr, unsigned long long* cand, unsigned int* cnt, unsigned int cap,

@@ -203,6 +203,14 @@ class TopKIndex:
                                               ctypes.byref(ol)))
         return ms.value, fl.value, ol.value
 
+    def profile_launches(self, cap=4096):
+        """Durations (ms) of the score-filter launches since the last profile_read, in launch order."""
+        buf = (ctypes.c_double * cap)()
+        n = ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_profile_launches(self._h, _stream(self.device), buf, cap, ctypes.byref(n)))
+        return [buf[i] for i in range(min(n.value, cap))]
+
     def debug_scores(self, queries):
         queries = _need(queries, torch.float32, "queries", 2)
         out = torch.zeros((self.n, queries.shape[0]), dtype=torch.float32, device=self.device)

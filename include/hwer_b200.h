@@ -98,6 +98,10 @@ int hwer_topk_finish(hwer_index_t* index, void* stream, uint32_t* needed_cap);
 int hwer_profile(hwer_index_t* index, int enable);
 int hwer_profile_read(hwer_index_t* index, void* stream, double* filter_ms, int64_t* filter_launches,
                       int64_t* other_launches);
+/* Per-launch view of the same events (call BEFORE hwer_profile_read, which resets them): the durations, in launch
+ * order, of the score-filter launches since the last read.  *n_out = number of launches recorded; at most `cap`
+ * are written to out_ms (milliseconds). */
+int hwer_profile_launches(hwer_index_t* index, void* stream, double* out_ms, int32_t cap, int32_t* n_out);
 
 /* Debug/validation aid: the full bf16 tensor-core score matrix out[n, ld] (ld >= B) for small problems. */
 int hwer_debug_scores(hwer_index_t* index, const float* queries_dev, int32_t B, float* out_dev, int64_t ld,

@@ -35,7 +35,7 @@ def main():
         for v in ("HWER_FIRST_ROWS", "HWER_GROWTH"):
             os.environ.pop(v, None)
         ref_idx = index.topk(q, a.k)[0].clone()
-        grid = [(None, None)] + [(f, gr) for f in (2048, 4096, 8192, 16384) for gr in (2, 4, 8, 16, 32, 64)]
+        grid = [(None, None)] + [(f, gr) for f in (2048, 4096, 8192, 16384) for gr in ((2, 3, 4, 6, 8) if B > 512 else (2, 4, 8, 16, 32, 64))]
         for first, growth in grid:
             for v, val in (("HWER_FIRST_ROWS", first), ("HWER_GROWTH", growth)):
                 if val is None:
