@@ -164,8 +164,8 @@ struct Schedule {
 // (scripts/tune_schedule.py, profiles/r01_v6_tune.txt).
 int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
     const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
-    long long first_rows = B > 512 ? 4096 : 8192;
-    int g = B <= 16 ? 32 : (B <= 128 ? 8 : (B <= 512 ? 4 : 2));
+    long long first_rows = (B > 512 || (B > 16 && B <= 128)) ? 4096 : 8192;
+    int g = B <= 16 ? 32 : (B <= 128 ? 16 : (B <= 512 ? 4 : 2));
     if (first_rows < 2LL * k) first_rows = 2LL * k;
     if (const char* e = getenv("HWER_FIRST_ROWS")) { long long v = atoll(e); if (v >= 2LL * k && v <= max_cap) first_rows = v; }   // tuning knob
     s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
