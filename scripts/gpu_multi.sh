@@ -2,7 +2,7 @@
 # bench.py at N GPUs with the peer-store exchange and with the NCCL all-gather for comparison.
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/t2_multi.log 2>&1; echo "t2 rc=$?" >> gpurun_out/t2_multi.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "two_gpu or peer_exchange or merge_and_shard" > gpurun_out/t2_multi.log 2>&1; echo "t2 rc=$?" >> gpurun_out/t2_multi.log
 tail -5 gpurun_out/t2_multi.log
 for EX in p2p nccl; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
