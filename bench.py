@@ -384,6 +384,15 @@ def run_b200(a):
     launches_per_step = (filt_l + other_l) / a.steps + (1 if world > 1 and a.exchange == "nccl" else 0)
     roof = roofline(a.batch, filt_ms / a.steps)
     roof["share_of_step"] = (filt_ms / a.steps) / (pms / a.steps)
+    if roof["bound"] == "tensor":
+        # which measured peak applies: the sustained (power-capped) cuBLAS figure when this run's SM clock was held
+        # well below its maximum during the timed region, the burst figure otherwise (short per-GPU steps at N > 1)
+        capped = bool(clocks) and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and \
+            clocks["sm_mhz"] < 0.93 * clocks["sm_max_mhz"]
+        if not capped or roof["frac"] > 1.0:
+            roof["peak"], roof["frac"] = roof["peak_burst"], roof["frac_of_burst"]
+            roof["basis"] = pk["basis"] + " (burst bf16: the SM clock was not held down by the power cap, or the " \
+                                          "kernel outran the sustained cuBLAS figure)"
 
     # ---- end to end through the public API: pinned host queries in, results out, every step
     q_host = queries_for(a.batch).cpu().pin_memory()
