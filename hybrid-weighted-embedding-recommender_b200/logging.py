@@ -1,12 +1,19 @@
-"""hwer/logging.py:1-13 -- same LOGLEVEL convention and record format."""
-import logging
-import os
+"""Logger factory with the reference's conventions (hwer/logging.py:1-13): level from the LOGLEVEL environment
+variable unless given, records tagged with pid, time, level and logger name."""
+import logging as _logging
+import os as _os
 
-FORMAT = '[PID: %(process)d] [%(asctime)s] [%(levelname)s] [%(name)s]: %(message)s'
-logging.basicConfig(format=FORMAT, level=os.environ.get("LOGLEVEL", "INFO"))
+_RECORD = "[PID: %(process)d] [%(asctime)s] [%(levelname)s] [%(name)s]: %(message)s"
+
+
+def _default_level():
+    return _os.environ.get("LOGLEVEL", "INFO")
+
+
+_logging.basicConfig(format=_RECORD, level=_default_level())
 
 
 def getLogger(name, level=None):
-    log = logging.getLogger(name)
-    log.setLevel(level if level is not None else os.environ.get("LOGLEVEL", "INFO"))
-    return log
+    logger = _logging.getLogger(name)
+    logger.setLevel(_default_level() if level is None else level)
+    return logger

@@ -160,24 +160,29 @@ def link_prediction_accuracy(model: RecommendationBase, nodes: List[Node], train
     return results
 
 
+def _pair_predictions(recsys, affinities):
+    """Scores of the (src, dst) pairs of `affinities` and their weights; NaN scores are an error (:259-267)."""
+    scores = np.asarray(recsys.predict([(e[0], e[1]) for e in map(tuple, affinities)]))
+    bad = np.isnan(scores)
+    if bad.any():
+        raise AssertionError("Encountered Nan Predictions = %s" % int(bad.sum()),
+                             [tuple(e) for e, b in zip(affinities, bad) if b])
+    return scores, np.array([tuple(e)[2] for e in affinities])
+
+
 def get_prediction_details(recsys, nodes: List[Node], train_affinities: List[Edge], validation_affinities: List[Edge],
                            model_get_topk=None, node_type: NodeType = "item"):
-    """hwer/validation.py:258-275."""
-    def get_details(recsys, affinities):
-        predictions = np.array(recsys.predict([(u, i) for u, i, r in affinities]))
-        if np.sum(np.isnan(predictions)) > 0:
-            count = np.sum(np.isnan(predictions))
-            raise AssertionError("Encountered Nan Predictions = %s" % count,
-                                 np.array(affinities)[np.isnan(predictions)])
-        actuals = np.array([r for u, i, r in affinities])
-        return predictions, actuals
+    """hwer/validation.py:258-275: pair scores of the validation edges, their weights, and one metric dict holding
+    the link-prediction metrics and extraction_efficiency's `metrics`."""
+    predictions, actuals = _pair_predictions(recsys, validation_affinities)
+    _pair_predictions(recsys, train_affinities)                 # the reference scores them too (NaN check only)
+    retrieval = extraction_efficiency(recsys, train_affinities, validation_affinities, model_get_topk, node_type)
+    stats = link_prediction_accuracy(recsys, nodes, train_affinities, validation_affinities)
+    stats.update(retrieval["metrics"])
+    return predictions, actuals, stats
 
-    predictions, actuals = get_details(recsys, validation_affinities)
-    train_predictions, _ = get_details(recsys, train_affinities)
-    ex_ee = extraction_efficiency(recsys, train_affinities, validation_affinities, model_get_topk, node_type)
-    lp_res = link_prediction_accuracy(recsys, nodes, train_affinities, validation_affinities)
-    lp_res.update(ex_ee["metrics"])
-    return predictions, actuals, lp_res
+
+_PROBE_IDS = ("eifjcchchbniufclvfdugvhnftdvjculhjitjihuncce", "eifjcchchbnirdjknkrvtfkbfurvjdfjhllbddtbvicb")
 
 
 def test_algorithm(train_affinities: List[Edge], validation_affinities: List[Edge],
@@ -186,32 +191,25 @@ def test_algorithm(train_affinities: List[Edge], validation_affinities: List[Edg
     """hwer/validation.py:190-222.  Training is outside this package: `hyperparameters` carries the trained tables
     (`vectors` for algo "content"; `collaborative_vectors` [+ `content_vectors`, `alpha`] for "gcn_ncf") next to
     `n_dims`; fit() picks them up from its `hyperparameters` keyword."""
-    from . import GcnNCF, ContentRecommendation
+    from . import ContentRecommendation, GcnNCF
     embedding_mapper, node_data = get_data_mappers()
-    kwargs = dict(hyperparameters=copy.copy(hyperparameters))
-    algo_map = dict(gcn_ncf=GcnNCF, content=ContentRecommendation)
-    recsys = algo_map[algo](embedding_mapper=embedding_mapper, node_types=node_types, n_dims=hyperparameters["n_dims"])
+    cls = {"gcn_ncf": GcnNCF, "content": ContentRecommendation}[algo]
+    recsys = cls(embedding_mapper=embedding_mapper, node_types=node_types, n_dims=hyperparameters["n_dims"])
+    t0 = time.time()
+    recsys.fit(nodes, train_affinities, node_data, hyperparameters=copy.copy(hyperparameters))
+    fit_seconds = time.time() - t0
 
-    start = time.time()
-    _ = recsys.fit(nodes, train_affinities, node_data, **kwargs)
-    end = time.time()
-    total_time = end - start
-
-    rnode = Node(list(node_types)[0], "eifjcchchbniufclvfdugvhnftdvjculhjitjihuncce")
-    rnode2 = Node(list(node_types)[0], "eifjcchchbnirdjknkrvtfkbfurvjdfjhllbddtbvicb")
-    default_preds = recsys.predict([(train_affinities[0].src, rnode),
-                                    (train_affinities[0].src, train_affinities[0].dst),
-                                    (rnode, rnode2),
-                                    (rnode2, train_affinities[0].src)])
+    # pairs with nodes that were never trained on must still score (to ~0.5), never NaN (:204-213)
+    some_type = list(node_types)[0]
+    ghost_a, ghost_b = (Node(some_type, i) for i in _PROBE_IDS)
+    first = train_affinities[0]
+    default_preds = recsys.predict([(first.src, ghost_a), (first.src, first.dst), (ghost_a, ghost_b), (ghost_b, first.src)])
     print("Default Preds = ", default_preds)
-    assert np.sum(np.isnan(default_preds)) == 0
+    assert not np.isnan(np.asarray(default_preds)).any()
 
-    res2 = {"algo": algo, "time": total_time}
     predictions, actuals, stats = get_prediction_details(recsys, nodes, train_affinities, validation_affinities,
                                                          model_get_topk, node_type)
-    res2.update(stats)
-    results = [res2]
-    return recsys, results, predictions, actuals
+    return recsys, [dict({"algo": algo, "time": fit_seconds}, **stats)], predictions, actuals
 
 
 test_algorithm.__test__ = False      # a harness entry point named like the reference's, not a pytest test
@@ -220,63 +218,62 @@ test_algorithm.__test__ = False      # a harness entry point named like the refe
 def test_multiple_algorithms(train_affinities, validation_affinities, nodes: List[Node], node_types: Set[NodeType],
                              hyperparamters_dict, get_data_mappers, algos, node_type: NodeType):
     """hwer/validation.py:225-240."""
-    results = []
-    recs = []
-    assert len(algos) > 0
-    algos = set(algos)
-    assert len(algos - {"content", "gcn_ncf"}) == 0
-    for algo in algos:
-        hyperparameters = hyperparamters_dict[algo]
-        rec, res, _, _ = test_algorithm(train_affinities, validation_affinities, nodes, node_types, hyperparameters,
-                                        get_data_mappers, algo, node_type)
-        results.extend(res)
+    wanted = set(algos)
+    assert wanted and wanted <= {"content", "gcn_ncf"}
+    recs, results = [], []
+    for algo in wanted:
+        rec, res, _, _ = test_algorithm(train_affinities, validation_affinities, nodes, node_types,
+                                        hyperparamters_dict[algo], get_data_mappers, algo, node_type)
         recs.append(rec)
+        results += res
     return recs, results
 
 
 test_multiple_algorithms.__test__ = False
 
 
+def _as_duration(seconds):
+    return str(datetime.timedelta(seconds=seconds))
+
+
 def display_results(results: List[Dict[str, Any]]):
-    """hwer/validation.py:243-255."""
+    """hwer/validation.py:243-255: per-algorithm means, printed eight columns at a time; returns the frame with
+    `retrieval_time` left numeric."""
     import pandas as pd
     from tabulate import tabulate
-    df = pd.DataFrame.from_records(results)
-    df = df.groupby(['algo']).mean()
-    df['time'] = df['time'].apply(lambda s: str(datetime.timedelta(seconds=s)))
-    t = df['retrieval_time']
-    df['retrieval_time'] = df['retrieval_time'].apply(lambda s: str(datetime.timedelta(seconds=s)))
-    cols = list(df.columns)
-    for c in [cols[i:i + 8] for i in range(0, len(cols), 8)]:
-        print(tabulate(df[c], headers='keys', tablefmt='psql'))
-    df['retrieval_time'] = t
-    return df
+    frame = pd.DataFrame.from_records(results).groupby("algo").mean()
+    seconds = frame["retrieval_time"].copy()
+    frame["time"] = frame["time"].map(_as_duration)
+    frame["retrieval_time"] = seconds.map(_as_duration)
+    names = list(frame.columns)
+    for first in range(0, len(names), 8):
+        print(tabulate(frame[names[first:first + 8]], headers="keys", tablefmt="psql"))
+    frame["retrieval_time"] = seconds
+    return frame
 
 
 def run_model_for_hpo(nodes: List[Node], edges: List[Tuple[Edge, bool]], node_types: Set[NodeType],
                       retrieved_node_type: NodeType, prepare_data_mappers, hyperparameters, algo):
     """hwer/validation.py:278-287."""
-    ndcg, ncf_ndcg = run_models_for_testing(nodes, edges, node_types, retrieved_node_type, prepare_data_mappers,
-                                            [algo], {algo: hyperparameters}, display=False)
-    return ndcg, ncf_ndcg
+    return run_models_for_testing(nodes, edges, node_types, retrieved_node_type, prepare_data_mappers, [algo],
+                                  {algo: hyperparameters}, display=False)
 
 
 def run_models_for_testing(nodes: List[Node], edges: List[Tuple[Edge, bool]], node_types: Set[NodeType],
                            retrieved_node_type: NodeType, prepare_data_mappers, algos, hyperparamters_dict,
                            display=True, results_csv="overall_results.csv"):
-    """hwer/validation.py:290-309: edges are (Edge, is_validation) pairs; returns (ndcg_b@100, ncf_ndcg)."""
+    """hwer/validation.py:290-309: `edges` are (Edge, is_validation) pairs; returns (ndcg_b@100, ncf_ndcg) of the
+    first algorithm.  display=True prints the table and writes it to `results_csv` (None: skip the file)."""
     import pandas as pd
-    train_affinities = [e for e, t in edges if not t]
-    validation_affinities = [e for e, t in edges if t]
-    recs, results = test_multiple_algorithms(train_affinities, validation_affinities, nodes, node_types,
-                                             hyperparamters_dict, prepare_data_mappers, algos, retrieved_node_type)
-    ndcg, ncf_ndcg = results[0]['ndcg_b@100'], results[0]['ncf_ndcg']
+    train = [e for e, held_out in edges if not held_out]
+    held = [e for e, held_out in edges if held_out]
+    _, results = test_multiple_algorithms(train, held, nodes, node_types, hyperparamters_dict, prepare_data_mappers,
+                                          algos, retrieved_node_type)
     if display:
-        results = display_results(results)
+        headline = results[0]["ndcg_b@100"], results[0]["ncf_ndcg"]
+        table = display_results(results)
         if results_csv:
-            results.to_csv(results_csv)
-    else:
-        results = pd.DataFrame.from_records(results)
-        results = results.groupby(["algo"]).mean().reset_index()
-        ndcg, ncf_ndcg = results["ndcg_b@100"].values[0], results["ncf_ndcg"].values[0]
-    return ndcg, ncf_ndcg
+            table.to_csv(results_csv)
+        return headline
+    means = pd.DataFrame.from_records(results).groupby("algo").mean().reset_index()
+    return means["ndcg_b@100"].values[0], means["ncf_ndcg"].values[0]
