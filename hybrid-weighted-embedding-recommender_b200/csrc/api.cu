@@ -162,7 +162,7 @@ struct Schedule {
 // is (DESIGN.md "Rounds").  A hit costs the epilogue far more than a miss, a round costs a launch plus a
 // select_compact pass, and both scale differently with the batch: the table below is measured on the C4 catalogue
 // (scripts/tune_schedule.py, profiles/r01_v6_tune.txt).
-int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
+int make_schedule(int B, int k, unsigned int cap_user, int world_share, Schedule* s) {
     const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
     long long first_rows = (B > 512 || (B > 16 && B <= 128)) ? 4096 : 8192;
     int g = B <= 16 ? 32 : (B <= 128 ? 16 : (B <= 512 ? 4 : 2));
@@ -181,6 +181,13 @@ int make_schedule(int B, int k, unsigned int cap_user, Schedule* s) {
     unsigned long long cap = 1024;
     while (cap < want) cap <<= 1;
     if (cap > max_cap) return fail(HWER_E_INVALID, "hwer_topk: k (or cap) too large for the shared-memory selector");
+    // Item shards that share thresholds every round (hwer_topk_sharded) each admit ~1/G of a round's candidates, so
+    // their rounds can grow G times faster for the same lists: a 1.25 M-row shard of an 8-way split needs 3 filter
+    // launches instead of 7, and every launch saved is ~100 us of extract + select + exchange on a ~2 ms step.
+    if (world_share > 1 && !getenv("HWER_GROWTH")) {
+        long long ge = (long long)g * world_share;
+        g = (int)(ge > 64 ? 64 : ge);
+    }
     s->growth = g;
     s->late_tiles = 1LL << 40;            // optional switch to plain doubling once this many tiles have been seen
     if (const char* e = getenv("HWER_LATE_ROWS")) s->late_tiles = atoll(e) / hwer::kTileItems;   // tuning knob
@@ -312,8 +319,9 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
     cudaStream_t stream = (cudaStream_t)stream_v;
     HWER_CUDA(cudaSetDevice(ix->device));
 
+    const int world_share = (xv && xv->world > 1) ? xv->world : 1;
     Schedule sch;
-    int rc = make_schedule(B, k, cap, &sch);
+    int rc = make_schedule(B, k, cap, world_share, &sch);
     if (rc) return rc;
     // bound the candidate workspace to ~1 GiB by chunking the query batch
     size_t chunk = ((size_t)1 << 30) / ((size_t)sch.cap * 8);
@@ -322,7 +330,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
     if (chunk > (size_t)B) chunk = B;
     rc = ensure_workspace(ix, chunk, sch.cap);
     if (rc) return rc;
-    rc = ensure_spill(ix, (int)chunk, k, sch.growth);
+    rc = ensure_spill(ix, (int)chunk, k, (sch.growth + world_share - 1) / world_share);
     if (rc) return rc;
     ix->last_cap = sch.cap;
 
