@@ -14,9 +14,8 @@
 //   UMMA N = nq <= 256 queries   (B operand: resident in shared memory for the CTA's lifetime)
 //   UMMA K = 16, d_pad/16 steps  (accumulators: fp32 in TMEM, acc_stages-deep)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
-// warps 2..17 = epilogue (tcgen05.ld -> release the accumulator -> sign test of score - thr -> rare append).
-#include <cstdlib>
-
+// warps 2..17 = epilogue (tcgen05.ld -> release the accumulator -> sign test of score - thr -> 48-byte spill entry
+// for a group of 8 columns with a hit; spill_extract_kernel behind the filter kernel appends the candidates).
 #include "common.cuh"
 #include "kernels.h"
 
