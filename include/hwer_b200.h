@@ -85,14 +85,18 @@ int hwer_index_destroy(hwer_index_t* index);
  * queries_dev [B, d] fp32 (any norm).  Results are ordered (score descending, row ascending); rows are local to
  * the index plus idx_offset; missing entries (fewer than k finite scores) are row -1 / score -inf.
  * cap = per-query candidate-list capacity (0 = automatic).  out_score64_dev may be NULL.
- * Asynchronous; call hwer_topk_finish before trusting the outputs. */
+ * Asynchronous; call hwer_topk_finish before trusting the outputs.
+ * The index owns its scratch memory and grows it on demand (the first call of a given batch size / k synchronises
+ * the device): candidate lists [min(B, chunk), cap] u64 (<= 1 GiB) and the filter rounds' spill buffers
+ * (58 - 465 MB: one 48-byte-entry append buffer per epilogue thread of the grid). */
 int hwer_topk(hwer_index_t* index, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
               int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev,
               void* stream);
 /* Synchronises `stream` and reports candidate-list overflow of the topk calls enqueued since the last finish. */
 int hwer_topk_finish(hwer_index_t* index, void* stream, uint32_t* needed_cap);
 
-/* Measurement aid: when enabled, every score-filter launch of hwer_topk is bracketed by CUDA events on the
+/* Measurement aid: when enabled, every score-filter launch of hwer_topk (with the spill-extract kernel that rides
+ * behind it) is bracketed by CUDA events on the
  * launching stream.  hwer_profile_read synchronises `stream`, returns the summed filter-kernel time and the
  * number of kernels launched (filter / everything else) since the last read, and resets the counters. */
 int hwer_profile(hwer_index_t* index, int enable);
