@@ -88,6 +88,12 @@ def ranking_metrics(model: RecommendationBase, users: List[Node], topk_rows: tor
     return res
 
 
+def _negative_pool(ordered_items, seen):
+    """Items the user has not interacted with, in the order of `ordered_items` -- the same list as
+    sorted(set(items) - seen, key=repr) when `ordered_items` is sorted by repr, without sorting per user."""
+    return [x for x in ordered_items if x not in seen]
+
+
 def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edges: List[Edge], item_list: List[Node]):
     item_list = set(item_list)
     interactions = defaultdict(set)
@@ -96,9 +102,9 @@ def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edge
     for u, i, _ in validation_edges:
         interactions[u].add(i)
     user_test_item = {}
+    ordered_items = sorted(item_list, key=repr)      # once, not per edge: the pools below keep this order
     for u, i, _ in validation_edges:     # one entry per user, the last validation edge wins (validation.py:79-81)
-        pool = sorted(item_list - interactions[u], key=repr)
-        user_test_item[u] = [i, *random.sample(pool, 100)]
+        user_test_item[u] = [i, *random.sample(_negative_pool(ordered_items, interactions[u]), 100)]
     if not user_test_item:
         return {"ncf_hr": float("nan"), "ncf_ndcg": float("nan")}
     users = list(user_test_item.keys())

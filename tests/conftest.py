@@ -71,3 +71,13 @@ def synthetic_edges(n_users, n_items, seed, val_per_user=3, min_train=5, max_tra
 @pytest.fixture(scope="session")
 def golden_lp():
     return np.load(os.path.join(GOLDEN, "reference_lp.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_c2():
+    return np.load(os.path.join(GOLDEN, "reference_c2.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_c3():
+    return np.load(os.path.join(GOLDEN, "reference_c3.npz"))

@@ -124,3 +124,45 @@ def test_partition_covers_rows_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_negative_pool_equals_per_user_sort():
+    """validation.ncf_eval samples its 100 negatives from sorted(items - seen, key=repr) (what the reference's
+    random.sample(set) amounts to under oracle/ref_shim.py); the pool is built by filtering one sorted list."""
+    import random
+    import hwer_b200 as hw
+    items = [hw.Node("item", i) for i in range(300)] + [hw.Node("item", "x%d" % i) for i in range(20)]
+    rnd = random.Random(3)
+    ordered = sorted(set(items), key=repr)
+    for _ in range(20):
+        seen = set(rnd.sample(items, rnd.randint(0, 150)))
+        assert hw.validation._negative_pool(ordered, seen) == sorted(set(items) - seen, key=repr)
+
+
+def test_ncf_eval_host_logic_with_a_stub_model():
+    """The host side of validation.ncf_eval (1 positive + 100 sampled negatives per user, rank of the positive ->
+    HR@10 / NDCG@10, hwer/validation.py:68-97) with the device scorer replaced by a table lookup."""
+    import random
+    import math
+    import torch
+    import hwer_b200 as hw
+    users = [hw.Node("user", i) for i in range(5)]
+    items = [hw.Node("item", i) for i in range(150)]
+    index = {n: j for j, n in enumerate(users + items)}
+
+    class Stub:
+        def _rows_of(self, nodes):
+            return torch.tensor([index[n] for n in nodes], dtype=torch.int64)
+
+        def predict_rows(self, src, dst):
+            # the user's positive (item id == user id) scores 0.9 for even users, 0.0 for odd ones; negatives 0.5
+            item = dst - len(users)
+            pos = item == src
+            return torch.where(pos, torch.where(src % 2 == 0, 0.9, 0.0), 0.5).float()
+
+    train = [hw.Edge(u, items[100 + j], 1.0) for j, u in enumerate(users)]
+    val = [hw.Edge(u, items[j], 1.0) for j, u in enumerate(users)]
+    random.seed(0)
+    out = hw.validation.ncf_eval(Stub(), train, val, items)
+    assert abs(out["ncf_hr"] - 3 / 5) < 1e-12                       # users 0, 2, 4 rank their positive first
+    assert abs(out["ncf_ndcg"] - (3 / 5) * (1.0 / math.log2(2.0)) / (1.0 + 1e-8)) < 1e-9

@@ -240,3 +240,54 @@ def test_c5_shard_properties_62m_top1000(hw):
     # batch independence: a query answered alone gives the same row
     i1, _, s1 = index.topk(q[1000:1001].contiguous(), k, idx_offset=off, want_f64=True)
     assert torch.equal(i1[0], idx[1000]) and torch.equal(s1[0], s64[1000])
+
+
+# ----------------------------------------------------------------------------- BASELINE.json configs[1] / configs[2]
+def test_c2_extraction_efficiency_matches_reference_run(hw, golden_c2):
+    """ML-1M shape, 6,040 x 3,706, d = 128: the whole validation.extraction_efficiency (top-200 for every user,
+    train items filtered, Recall@K / NDCG / diversity) against the metrics the reference produced on the same
+    seeded inputs (58.7 s there, hwer/validation.py:100-187)."""
+    import time
+    nu, ni, dd = [int(x) for x in golden_c2["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, int(golden_c2["seeds"][0]))
+    users = [hw.Node("user", i) for i in range(nu)]
+    items = [hw.Node("item", i) for i in range(ni)]
+    tr, vl = synthetic_edges(nu, ni, int(golden_c2["seeds"][1]))
+    train = [hw.Edge(users[u], items[i], w) for u, i, w in tr]
+    val = [hw.Edge(users[u], items[i], w) for u, i, w in vl]
+    m = hw.ContentRecommendation(None, {"user", "item"}, n_dims=dd)
+    m.fit(users + items, train, None, vectors=O.unit_length(collab, axis=1))
+    random.seed(0)
+    t0 = time.time()
+    res = hw.validation.extraction_efficiency(m, train, val, hw.validation.model_get_topk, "item")
+    print("C2 extraction_efficiency: %.2f s (retrieval %.4f s; the reference: 58.7 s / %.1f s)"
+          % (time.time() - t0, res["metrics"]["retrieval_time"], float(golden_c2["retrieval_time"][0])))
+    ref = dict(zip([str(k) for k in golden_c2["metric_keys"]], golden_c2["metric_values"]))
+    for key, v in ref.items():
+        assert abs(res["metrics"][key] - v) < 1e-9, (key, res["metrics"][key], v)
+    # a few users' filtered top-100 lists, id for id
+    rows = res["rows"].cpu().numpy()
+    pos = {u: j for j, u in enumerate(res["users"])}
+    train_items = {}
+    for u, i, w in tr:
+        train_items.setdefault(u, set()).add(i)
+    for u, want in zip(golden_c2["sample_users"], golden_c2["sample_preds"]):
+        got = [int(r) - nu for r in rows[pos[users[int(u)]]] if int(r) - nu not in train_items.get(int(u), ())][:100]
+        assert got == [int(x) for x in want if x >= 0], int(u)
+
+
+def test_c3_find_closest_neighbours_matches_reference_run(hw, golden_c3):
+    """ML-20M item side, 27,278 x 256: top-100 for 96 user and 16 item anchors, ids and scores of the reference."""
+    nu, ni, dd, k = [int(x) for x in golden_c3["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, int(golden_c3["seed"][0]))
+    users = [hw.Node("user", i) for i in range(nu)]
+    items = [hw.Node("item", i) for i in range(ni)]
+    edges = [hw.Edge(users[i % nu], items[i], 1.0) for i in range(10)]
+    m = hw.ContentRecommendation(None, {"user", "item"}, n_dims=dd)
+    m.fit(users + items, edges, None, vectors=O.unit_length(collab, axis=1))
+    for anchors, nodes, key in ((golden_c3["user_anchors"], users, "user"), (golden_c3["item_anchors"], items, "item")):
+        rows, scores = m.find_closest_neighbours_batch("item", [nodes[int(a)] for a in anchors], k=k)
+        np.testing.assert_array_equal(rows.cpu().numpy() - nu, golden_c3[key + "_idx"])
+        np.testing.assert_allclose(scores.cpu().numpy(), golden_c3[key + "_score"], rtol=0, atol=1e-6)
+    one = m.find_similar_items(items[int(golden_c3["item_anchors"][0])], k=k)
+    assert [int(n.node_external_id) for n, s in one] == [int(x) for x in golden_c3["item_idx"][0]]

@@ -211,3 +211,46 @@ def test_average_precision_restatement_equals_sklearn_with_ties():
         y[0] = 1
         s = rs.randint(0, levels, n).astype(np.float32) / levels
         assert abs(O.average_precision_score(y, s) - average_precision_score(y, s)) < 1e-12
+
+
+# ----------------------------------------------------------------------------- configs C2 / C3 (BASELINE.json)
+def test_c2_extraction_metrics_match_reference(golden_c2):
+    """ML-1M shape (6,040 x 3,706, d = 128): the oracle's restatement of validation.extraction_efficiency against the
+    reference's own run (58.7 s there; candidates come from the brute-force exact_topk here, which
+    test_exact_topk_equals_reference_order ties to the KD-tree's answers)."""
+    nu, ni, dd = [int(x) for x in golden_c2["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, seed=int(golden_c2["seeds"][0]))
+    table = O.unit_length(collab, axis=1)
+    users = [O.Node("user", i) for i in range(nu)]
+    items = [O.Node("item", i) for i in range(ni)]
+    tr, vl = synthetic_edges(nu, ni, seed=int(golden_c2["seeds"][1]))
+    train = [(users[u], items[i], w) for u, i, w in tr]
+    val = [(users[u], items[i], w) for u, i, w in vl]
+    idx, sc = O.exact_topk(table[nu:], table[:nu], 200)
+    preds = {users[u]: [(items[int(i)], (float(s) + 1) / 2) for i, s in zip(idx[u], sc[u])] for u in range(nu)}
+    out = O.extraction_metrics(preds, train, val, "item", cutoffs=(10, 100))
+    ref = dict(zip([str(k) for k in golden_c2["metric_keys"]], golden_c2["metric_values"]))
+    for key in ("recall@100", "ndcg_b@100", "ndcg_b@10", "recall@10", "diversity"):
+        assert abs(out[key] - ref[key]) < 1e-12, (key, out[key], ref[key])
+
+
+def test_c3_find_closest_neighbours_matches_reference(golden_c3):
+    """ML-20M item side (27,278 x 256): top-100 for user and item anchors, ids and scores of the reference's run."""
+    nu, ni, dd, k = [int(x) for x in golden_c3["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, seed=int(golden_c3["seed"][0]))
+    table = O.unit_length(collab, axis=1)
+    users = [O.Node("user", i) for i in range(nu)]
+    items = [O.Node("item", i) for i in range(ni)]
+    m = O.OracleRecommender({"user", "item"}, n_dims=dd)
+    m.add_nodes(users + items)
+    m.build_knn(table)
+    for anchors, nodes, key in ((golden_c3["user_anchors"][:24], users, "user"), (golden_c3["item_anchors"][:8], items, "item")):
+        for j, a in enumerate(anchors):
+            got = m.find_closest_neighbours("item", nodes[int(a)], k=k)
+            ids = [int(n.node_external_id) for n, s in got]
+            assert ids == [int(x) for x in golden_c3[key + "_idx"][j]]
+            np.testing.assert_allclose([s for n, s in got], golden_c3[key + "_score"][j], rtol=0, atol=1e-6)
+    # the brute-force order is the KD-tree's order (no ties at this shape)
+    ua = golden_c3["user_anchors"]
+    idx, sc = O.exact_topk(table[nu:], table[ua], k)
+    np.testing.assert_array_equal(idx, golden_c3["user_idx"])
