@@ -27,44 +27,61 @@ FeatureName = str
 
 
 class Node:
+    """(node_type, node_external_id) value object of hwer/recommendation_base.py:19-36: equal and hashed by that
+    pair, external ids compared as strings, repr = the pair.  The pair and its hash are computed once: nodes key
+    every host-side dict of this package (a 10 M-node table does tens of millions of lookups per evaluation)."""
+
     def __init__(self, node_type, node_external_id):
         self.node_type = node_type
         self.node_external_id = str(node_external_id)
-
-    def __key(self):
-        return (self.node_type, self.node_external_id)
+        self._pair = (self.node_type, self.node_external_id)
+        self._pair_hash = hash(self._pair)
 
     def __hash__(self):
-        return hash(self.__key())
+        return self._pair_hash
 
     def __eq__(self, other):
         if isinstance(other, Node):
-            return self.__key() == other.__key()
+            return self._pair == other._pair
         return NotImplemented
 
+    def __getstate__(self):
+        # string hashes are per process (PYTHONHASHSEED): never carry the cached hash across a pickle
+        state = dict(self.__dict__)
+        state.pop("_pair_hash", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._pair = (self.node_type, self.node_external_id)
+        self._pair_hash = hash(self._pair)
+
     def __repr__(self):
-        return str(self.__key())
+        return str(self._pair)
 
 
 class Edge:
+    """(src, dst, weight) of hwer/recommendation_base.py:39-61; iterating yields the three fields, so
+    `for u, i, r in edges` works as in the reference."""
+
     def __init__(self, src: Node, dst: Node, weight: float):
         self.src = src
         self.dst = dst
         self.weight = weight
         self.contents = [src, dst, weight]
 
-    def __key(self):
+    def _triple(self):
         return (self.src, self.dst, self.weight)
 
     def __iter__(self):
         return iter(self.contents)
 
     def __hash__(self):
-        return hash(self.__key())
+        return hash(self._triple())
 
     def __eq__(self, other):
         if isinstance(other, Edge):
-            return self.__key() == other.__key()
+            return self._triple() == other._triple()
         return NotImplemented
 
     def __repr__(self):

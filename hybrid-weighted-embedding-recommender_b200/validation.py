@@ -94,22 +94,47 @@ def _negative_pool(ordered_items, seen):
     return [x for x in ordered_items if x not in seen]
 
 
+def _sample_negatives(validation_edges, interactions, ordered_items):
+    """For every validation edge, 100 items the edge's user never touched, drawn like
+    random.sample(sorted(items - seen, key=repr), 100) (validation.py:80 under Python >= 3.11, where sampling
+    from a set needs an order): same draws from the `random` module, same picks, but the pool is a numpy index
+    vector -- random.sample(range(n), k) returns the positions random.sample(pool, k) would read.  Returns
+    {user: (positive item, [100 positions into ordered_items])}; one entry per user, the last edge wins (:79-81)."""
+    n_items = len(ordered_items)
+    position = {it: j for j, it in enumerate(ordered_items)}
+    seen_positions = {}
+    out = {}
+    for u, i, _ in validation_edges:
+        sp = seen_positions.get(u)
+        if sp is None:
+            sp = np.fromiter((position[x] for x in interactions[u] if x in position), dtype=np.int64)
+            seen_positions[u] = sp
+        free = np.ones(n_items, dtype=bool)
+        free[sp] = False
+        pool = np.flatnonzero(free)
+        out[u] = (i, pool[random.sample(range(pool.shape[0]), 100)])
+    return out
+
+
 def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edges: List[Edge], item_list: List[Node]):
-    item_list = set(item_list)
+    """hwer/validation.py:68-97: per validation user 1 positive + 100 sampled negatives, scored by the model,
+    HR@10 and binary NDCG@10 of the positive's rank.  All 101 x users pairs are scored in one device call."""
     interactions = defaultdict(set)
     for u, i, _ in train_edges:
         interactions[u].add(i)
     for u, i, _ in validation_edges:
         interactions[u].add(i)
-    user_test_item = {}
-    ordered_items = sorted(item_list, key=repr)      # once, not per edge: the pools below keep this order
-    for u, i, _ in validation_edges:     # one entry per user, the last validation edge wins (validation.py:79-81)
-        user_test_item[u] = [i, *random.sample(_negative_pool(ordered_items, interactions[u]), 100)]
-    if not user_test_item:
+    ordered_items = sorted(set(item_list), key=repr)
+    picks = _sample_negatives(validation_edges, interactions, ordered_items)
+    if not picks:
         return {"ncf_hr": float("nan"), "ncf_ndcg": float("nan")}
-    users = list(user_test_item.keys())
-    src = model._rows_of([u for u in users for _ in range(101)])
-    dst = model._rows_of([it for u in users for it in user_test_item[u]])
+    users = list(picks.keys())
+    item_rows = model._rows_of(ordered_items)                                   # rows of the candidate items, once
+    user_rows = model._rows_of(users)
+    pos_rows = model._rows_of([picks[u][0] for u in users])
+    neg_pos = torch.from_numpy(np.stack([picks[u][1] for u in users])).to(item_rows.device)     # [U, 100]
+    dst = torch.cat([pos_rows[:, None], item_rows[neg_pos]], dim=1).reshape(-1).contiguous()   # positive first
+    src = user_rows[:, None].expand(len(users), 101).reshape(-1).contiguous()
     s = model.predict_rows(src, dst).reshape(len(users), 101)
     # stable descending sort keeps the positive (column 0) ahead of equal-scored negatives (validation.py:85)
     rank = (s[:, 1:] > s[:, :1]).sum(dim=1)

@@ -1,6 +1,7 @@
 """CPU: the C-ABI library loads and exports every symbol include/hwer_b200.h declares; the host-side mirror keeps
 the reference's semantics; nothing silently falls back to the CPU."""
 import os
+import sys
 import re
 
 import numpy as np
@@ -126,17 +127,37 @@ def test_partition_covers_rows_exactly():
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
 
 
-def test_negative_pool_equals_per_user_sort():
-    """validation.ncf_eval samples its 100 negatives from sorted(items - seen, key=repr) (what the reference's
-    random.sample(set) amounts to under oracle/ref_shim.py); the pool is built by filtering one sorted list."""
+def test_sampled_negatives_equal_sampling_from_the_sorted_pool():
+    """validation.ncf_eval draws its 100 negatives like random.sample(sorted(items - seen, key=repr), 100) (what the
+    reference's random.sample(set) amounts to under oracle/ref_shim.py), but from a numpy index vector: same
+    consumption of the `random` stream, same picks."""
     import random
+    from collections import defaultdict
     import hwer_b200 as hw
     items = [hw.Node("item", i) for i in range(300)] + [hw.Node("item", "x%d" % i) for i in range(20)]
+    users = [hw.Node("user", i) for i in range(12)]
     rnd = random.Random(3)
+    interactions = defaultdict(set)
+    val = []
+    for u in users:
+        interactions[u] = set(rnd.sample(items, rnd.randint(1, 150))) | {hw.Node("genre", "g")}
+        for it in rnd.sample(sorted(interactions[u] - {hw.Node("genre", "g")}, key=repr), 2):    # two edges per user
+            val.append((u, it, 1.0))
     ordered = sorted(set(items), key=repr)
-    for _ in range(20):
-        seen = set(rnd.sample(items, rnd.randint(0, 150)))
-        assert hw.validation._negative_pool(ordered, seen) == sorted(set(items) - seen, key=repr)
+    random.seed(9)
+    got = hw.validation._sample_negatives(val, interactions, ordered)
+    random.seed(9)
+    want = {}
+    for u, i, _ in val:
+        want[u] = (i, random.sample(sorted(set(items) - interactions[u], key=repr), 100))
+    state_after = random.getstate()
+    assert set(got) == set(want)
+    for u in want:
+        assert got[u][0] == want[u][0]
+        assert [ordered[j] for j in got[u][1]] == want[u][1]
+    random.seed(9)
+    hw.validation._sample_negatives(val, interactions, ordered)
+    assert random.getstate() == state_after            # the stream is consumed exactly like the restatement's
 
 
 def test_ncf_eval_host_logic_with_a_stub_model():
@@ -166,3 +187,19 @@ def test_ncf_eval_host_logic_with_a_stub_model():
     out = hw.validation.ncf_eval(Stub(), train, val, items)
     assert abs(out["ncf_hr"] - 3 / 5) < 1e-12                       # users 0, 2, 4 rank their positive first
     assert abs(out["ncf_ndcg"] - (3 / 5) * (1.0 / math.log2(2.0)) / (1.0 + 1e-8)) < 1e-9
+
+
+def test_node_hash_is_recomputed_after_pickling_into_another_process():
+    """Node caches hash((type, id)); string hashes differ between processes, so the cache must not travel."""
+    import pickle
+    import subprocess
+    import hwer_b200 as hw
+    blob = pickle.dumps([hw.Node("user", 3), hw.Node("item", "abc")])
+    code = ("import sys, pickle; sys.path.insert(0, %r); import hwer_b200 as hw; "
+            "a, b = pickle.loads(sys.stdin.buffer.read()); "
+            "assert a == hw.Node('user', '3') and hash(a) == hash(hw.Node('user', 3)); "
+            "assert {hw.Node('item', 'abc'): 1}[b] == 1; print('ok')" % ROOT)
+    for seed in ("1", "2"):
+        r = subprocess.run([sys.executable, "-c", code], input=blob, capture_output=True,
+                           env=dict(os.environ, PYTHONHASHSEED=seed))
+        assert r.returncode == 0 and b"ok" in r.stdout, r.stderr.decode()[-500:]
