@@ -20,6 +20,7 @@ IPC_HANDLE_BYTES = 64
 PHASE_SEARCH, PHASE_MERGE, PHASE_COLLECT, PHASE_ALL = 1, 2, 4, 7
 MODE_EXACT = 0
 MODE_BF16 = 1
+SCORE_PAIR, SCORE_DIST, SCORE_GIVEN, SCORE_EUCLID = 0, 1, 2, 3
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header is exported
 SIGNATURES = {
@@ -34,6 +35,8 @@ SIGNATURES = {
     "hwer_index_destroy": (c_int, [c_void_p]),
     "hwer_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_uint32, c_int64, c_void_p, c_void_p,
                           c_void_p, c_void_p]),
+    "hwer_topk_exhaustive": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
     "hwer_topk_finish": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
     "hwer_profile": (c_int, [c_void_p, c_int]),
     "hwer_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
@@ -54,6 +57,12 @@ SIGNATURES = {
     "hwer_pair_score": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hwer_compose_queries": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_void_p, c_void_p]),
+    "hwer_average_embeddings": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "hwer_gather_rows": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "hwer_map_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "hwer_rerank": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hwer_hit_rank_metrics": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "hwer_ncf_param_count": (c_int64, [c_int32, c_int32]),
     "hwer_ncf_score": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                c_void_p]),

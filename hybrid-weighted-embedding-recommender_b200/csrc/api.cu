@@ -80,6 +80,10 @@ struct hwer_index {
     unsigned int* needed_dev = nullptr;
     unsigned int* needed_host = nullptr;   // pinned
     unsigned int last_cap = 0;
+    unsigned int* ovf = nullptr;           // [ws_queries] sticky per-query "candidate list overflowed" marks of a call
+    // tuning knobs (HWER_FIRST_ROWS / HWER_GROWTH / HWER_LATE_ROWS), read once when the index is created
+    long long env_first_rows = 0, env_late_rows = 0;
+    int env_growth = 0;
     // optional live profiling of the dominant (filter) kernel with CUDA events on the launching stream
     bool prof = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
@@ -91,19 +95,24 @@ namespace {
 
 int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
     if (queries <= ix->ws_queries && cap <= ix->ws_cap) return HWER_OK;
+    // grow-only in each dimension (alternating call shapes must not reallocate on every call), bounded by the
+    // ~1 GiB the chunking of topk_impl aims at: when the product would exceed it, keep exactly what is asked for
+    size_t q = queries > ix->ws_queries ? queries : ix->ws_queries;
+    size_t c = cap > ix->ws_cap ? cap : ix->ws_cap;
+    if (q * c * sizeof(unsigned long long) > ((size_t)5 << 28)) { q = queries; c = cap; }
     HWER_CUDA(cudaDeviceSynchronize());
     if (ix->cand) cudaFree(ix->cand);
     if (ix->cnt) cudaFree(ix->cnt);
     if (ix->thr) cudaFree(ix->thr);
     if (ix->margin) cudaFree(ix->margin);
     if (ix->floor) cudaFree(ix->floor);
-    ix->floor = nullptr;
+    if (ix->ovf) cudaFree(ix->ovf);
+    ix->floor = nullptr; ix->ovf = nullptr;
     ix->cand = nullptr; ix->cnt = nullptr; ix->thr = nullptr; ix->margin = nullptr;
     ix->ws_queries = ix->ws_cap = 0;
-    const size_t q = queries > ix->ws_queries ? queries : ix->ws_queries;
-    const size_t c = cap > ix->ws_cap ? cap : ix->ws_cap;
     if (cudaMalloc(&ix->cand, q * c * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ix->cnt, q * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&ix->ovf, q * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&ix->thr, q * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&ix->margin, q * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&ix->floor, q * sizeof(float)) != cudaSuccess) {
@@ -122,7 +131,7 @@ int ensure_spill(hwer_index* ix, int Bc, int k, int growth) {
     const double per_thread = 1.4 * k * growth * (double)Bc / (double)hwer::filter_tc_spill_buffers(ix->num_sms);
     int want = 16;
     while (want < 2.0 * per_thread + 8.0 && want < 128) want <<= 1;
-    if (want <= ix->spill_cap) return HWER_OK;
+    if (want <= ix->spill_cap) return HWER_OK;      // grow-only: a larger buffer serves every smaller request
     HWER_CUDA(cudaDeviceSynchronize());
     if (ix->spill) cudaFree(ix->spill);
     if (ix->spill_cnt) cudaFree(ix->spill_cnt);
@@ -162,16 +171,16 @@ struct Schedule {
 // is (DESIGN.md "Rounds").  A hit costs the epilogue far more than a miss, a round costs a launch plus a
 // select_compact pass, and both scale differently with the batch: the table below is measured on the C4 catalogue
 // (scripts/tune_schedule.py, profiles/r01_v6_tune.txt).
-int make_schedule(int B, int k, unsigned int cap_user, int world_share, Schedule* s) {
+int make_schedule(const hwer_index* ix, int B, int k, unsigned int cap_user, int world_share, Schedule* s) {
     const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
     long long first_rows = (B > 512 || (B > 16 && B <= 128)) ? 4096 : 8192;
     int g = B <= 16 ? 32 : (B <= 128 ? 16 : (B <= 512 ? 4 : 2));
     if (first_rows < 2LL * k) first_rows = 2LL * k;
-    if (const char* e = getenv("HWER_FIRST_ROWS")) { long long v = atoll(e); if (v >= 2LL * k && v <= max_cap) first_rows = v; }   // tuning knob
+    if (ix->env_first_rows >= 2LL * k && ix->env_first_rows <= max_cap) first_rows = ix->env_first_rows;   // tuning knob
     s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
     first_rows = s->first_tiles * hwer::kTileItems;
     while (g > 1 && 3LL * k * g > max_cap) g >>= 1;
-    if (const char* e = getenv("HWER_GROWTH")) { int v = atoi(e); if (v >= 1 && 3LL * k * v <= max_cap) g = v; }   // tuning knob
+    if (ix->env_growth >= 1 && 3LL * k * ix->env_growth <= max_cap) g = ix->env_growth;   // tuning knob
     unsigned long long want = 3ULL * k * g;
     if (want < (unsigned long long)first_rows) want = first_rows;
     if (cap_user) {
@@ -184,13 +193,13 @@ int make_schedule(int B, int k, unsigned int cap_user, int world_share, Schedule
     // Item shards that share thresholds every round (hwer_topk_sharded) each admit ~1/G of a round's candidates, so
     // their rounds can grow G times faster for the same lists: a 1.25 M-row shard of an 8-way split needs 3 filter
     // launches instead of 7, and every launch saved is ~100 us of extract + select + exchange on a ~2 ms step.
-    if (world_share > 1 && !getenv("HWER_GROWTH")) {
+    if (world_share > 1 && ix->env_growth < 1) {
         long long ge = (long long)g * world_share;
         g = (int)(ge > 64 ? 64 : ge);
     }
     s->growth = g;
     s->late_tiles = 1LL << 40;            // optional switch to plain doubling once this many tiles have been seen
-    if (const char* e = getenv("HWER_LATE_ROWS")) s->late_tiles = atoll(e) / hwer::kTileItems;   // tuning knob
+    if (ix->env_late_rows > 0) s->late_tiles = ix->env_late_rows / hwer::kTileItems;   // tuning knob
     s->cap = (unsigned int)cap;
     return HWER_OK;
 }
@@ -278,6 +287,9 @@ int hwer_index_create(hwer_index_t** out, const float* table_f32_dev, const void
     }
     cudaMemset(ix->needed_dev, 0, sizeof(unsigned int));
     *ix->needed_host = 0;
+    if (const char* e = getenv("HWER_FIRST_ROWS")) ix->env_first_rows = atoll(e);
+    if (const char* e = getenv("HWER_GROWTH")) ix->env_growth = atoi(e);
+    if (const char* e = getenv("HWER_LATE_ROWS")) ix->env_late_rows = atoll(e);
     *out = ix;
     return HWER_OK;
 }
@@ -291,6 +303,7 @@ int hwer_index_destroy(hwer_index_t* ix) {
     if (ix->thr) cudaFree(ix->thr);
     if (ix->margin) cudaFree(ix->margin);
     if (ix->floor) cudaFree(ix->floor);
+    if (ix->ovf) cudaFree(ix->ovf);
     if (ix->spill) cudaFree(ix->spill);
     if (ix->spill_cnt) cudaFree(ix->spill_cnt);
     if (ix->needed_dev) cudaFree(ix->needed_dev);
@@ -321,7 +334,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
 
     const int world_share = (xv && xv->world > 1) ? xv->world : 1;
     Schedule sch;
-    int rc = make_schedule(B, k, cap, world_share, &sch);
+    int rc = make_schedule(ix, B, k, cap, world_share, &sch);
     if (rc) return rc;
     // bound the candidate workspace to ~1 GiB by chunking the query batch
     size_t chunk = ((size_t)1 << 30) / ((size_t)sch.cap * 8);
@@ -351,6 +364,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         const int Bc = (int)(((long long)B - q0) < (long long)chunk ? ((long long)B - q0) : (long long)chunk);
         const float* Q = queries_dev + (size_t)q0 * ix->d;
         HWER_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(unsigned int) * Bc, stream));
+        HWER_CUDA(cudaMemsetAsync(ix->ovf, 0, sizeof(unsigned int) * Bc, stream));
         HWER_CUDA(hwer::launch_fill_f32(ix->thr, Bc, -INFINITY, stream));
         // the CUDA-core path scores in fp32: its (tiny) margin keeps even bf16-less indexes exact
         const float* margin = (exact || !ix->use_tc) ? ix->margin : nullptr;
@@ -401,15 +415,15 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 for (int r = 0; r < xv->world; ++r) sx.thr_x[r] = xv->thr_x[r];
                 sx.mode = hwer::kSelKthToPeers;
                 HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k_share, fixed, margin, ix->thr,
-                                                      ix->needed_dev, &sx, stream));
+                                                      ix->needed_dev, ix->ovf, &sx, stream));
                 HWER_CUDA(hwer::launch_exchange_signal(*xv, 4, sx.epoch, stream));
                 sx.mode = hwer::kSelCompactMin;
                 HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
-                                                      ix->needed_dev, &sx, stream));
+                                                      ix->needed_dev, ix->ovf, &sx, stream));
                 ix->other_launches += 2;
             } else {
                 HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
-                                                      ix->needed_dev, nullptr, stream));
+                                                      ix->needed_dev, ix->ovf, nullptr, stream));
             }
             ix->filter_launches += 1;
             ix->other_launches += 1;
@@ -422,7 +436,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                                      peer ? nullptr : (long long*)out_idx_dev + (size_t)q0 * k,
                                      peer ? nullptr : out_score_dev + (size_t)q0 * k,
                                      (!peer && out_score64_dev) ? out_score64_dev + (size_t)q0 * k : nullptr,
-                                     ix->needed_dev, peer ? &pd : nullptr, stream));
+                                     ix->needed_dev, ix->ovf, peer ? &pd : nullptr, stream));
     }
     return HWER_OK;
 }
@@ -596,6 +610,31 @@ int hwer_exchange_error(hwer_exchange_t* x, void* stream_v) {
     return HWER_OK;
 }
 
+int hwer_topk_exhaustive(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, int64_t idx_offset,
+                         int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream_v) {
+    if (!ix || B < 0 || k <= 0 || (B > 0 && (!queries_dev || !out_idx_dev || !out_score_dev)))
+        return fail(HWER_E_INVALID, "hwer_topk_exhaustive: bad argument");
+    if ((long long)k > ix->n) return fail(HWER_E_K_TOO_LARGE, "hwer_topk_exhaustive: k exceeds the number of rows in the index");
+    if (B == 0) return HWER_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    HWER_CUDA(cudaSetDevice(ix->device));
+    const size_t bytes = hwer::bruteforce_scratch_bytes(ix->n);
+    void* scratch = nullptr;
+    if (cudaMallocAsync(&scratch, bytes, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HWER_E_NOMEM, "hwer_topk_exhaustive: cannot allocate the sort scratch");
+    }
+    cudaError_t e = cudaSuccess;
+    for (int q = 0; q < B && e == cudaSuccess; ++q)
+        e = hwer::launch_bruteforce_topk(ix->table, ix->n, ix->d, queries_dev + (size_t)q * ix->d, k, idx_offset,
+                                         (long long*)out_idx_dev + (size_t)q * k, out_score_dev + (size_t)q * k,
+                                         out_score64_dev ? out_score64_dev + (size_t)q * k : nullptr, scratch, bytes,
+                                         stream);
+    cudaFreeAsync(scratch, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "hwer_topk_exhaustive");
+    return HWER_OK;
+}
+
 int hwer_topk_finish(hwer_index_t* ix, void* stream_v, uint32_t* needed_cap) {
     if (!ix) return fail(HWER_E_INVALID, "hwer_topk_finish: null index");
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -700,6 +739,61 @@ int hwer_compose_queries(const float* table_dev, int64_t n, int32_t d, const int
                                            (const long long*)pos_ptr_dev, (const long long*)pos_rows_dev,
                                            (const long long*)neg_ptr_dev, (const long long*)neg_rows_dev, B, out_dev,
                                            (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_average_embeddings(const float* table_dev, int64_t n, int32_t d, const int64_t* ptr_dev,
+                            const int64_t* rows_dev, int32_t L, float* out_dev, void* stream) {
+    if (!table_dev || n <= 0 || d <= 0 || d > 1024 || L < 0 || (L > 0 && (!ptr_dev || !rows_dev || !out_dev)))
+        return fail(HWER_E_INVALID, "hwer_average_embeddings: bad argument (d <= 1024)");
+    HWER_CUDA(hwer::launch_average_embeddings(table_dev, n, d, (const long long*)ptr_dev, (const long long*)rows_dev, L,
+                                              out_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_gather_rows(const float* table_dev, int64_t n, int32_t d, const int64_t* rows_dev, int64_t P, float* out_dev,
+                     void* stream) {
+    if (!table_dev || n <= 0 || d <= 0 || P < 0 || (P > 0 && (!rows_dev || !out_dev)))
+        return fail(HWER_E_INVALID, "hwer_gather_rows: bad argument");
+    HWER_CUDA(hwer::launch_gather_rows(table_dev, n, d, (const long long*)rows_dev, P, out_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_map_rows(const int64_t* rows_dev, int64_t count, const int64_t* row_map_dev, int64_t offset, int64_t* out_dev,
+                  void* stream) {
+    if (count < 0 || (count > 0 && (!rows_dev || !out_dev))) return fail(HWER_E_INVALID, "hwer_map_rows: bad argument");
+    HWER_CUDA(hwer::launch_map_rows((const long long*)rows_dev, count, (const long long*)row_map_dev, offset,
+                                    (long long*)out_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_rerank(const float* table_dev, int64_t n, int32_t d, const int64_t* rows_dev, const int64_t* row_map_dev,
+                int32_t B, int32_t k, int32_t convention, const int64_t* anchor_rows_dev, const float* queries_dev,
+                const float* given_dev, int64_t* out_rows_dev, double* out_score_dev, void* stream) {
+    if (!table_dev || n <= 0 || d <= 0 || B < 0 || k <= 0 || k > 8192 ||
+        (B > 0 && (!rows_dev || !out_rows_dev || !out_score_dev)))
+        return fail(HWER_E_INVALID, "hwer_rerank: bad argument (0 < k <= 8192)");
+    if (convention < HWER_SCORE_PAIR || convention > HWER_SCORE_EUCLID)
+        return fail(HWER_E_INVALID, "hwer_rerank: unknown score convention");
+    if (B > 0 && ((convention == HWER_SCORE_PAIR && !anchor_rows_dev) || (convention == HWER_SCORE_GIVEN && !given_dev) ||
+                  ((convention == HWER_SCORE_DIST || convention == HWER_SCORE_EUCLID) && !queries_dev)))
+        return fail(HWER_E_INVALID, "hwer_rerank: the input of this score convention is missing");
+    HWER_CUDA(hwer::launch_rerank(table_dev, n, d, (const long long*)rows_dev, (const long long*)row_map_dev, B, k,
+                                  convention, (const long long*)anchor_rows_dev, queries_dev, given_dev,
+                                  (long long*)out_rows_dev, out_score_dev, (cudaStream_t)stream));
+    return HWER_OK;
+}
+
+int hwer_hit_rank_metrics(const float* scores_dev, int32_t U, int32_t M, int32_t topn, double* out2_dev,
+                          int32_t* rank_dev, void* stream_v) {
+    if (!scores_dev || U <= 0 || M < 0 || topn <= 0 || !out2_dev)
+        return fail(HWER_E_INVALID, "hwer_hit_rank_metrics: bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int* rank = rank_dev;
+    if (!rank) HWER_CUDA(cudaMallocAsync(&rank, sizeof(int) * (size_t)U, stream));
+    cudaError_t e = hwer::launch_hit_rank(scores_dev, U, M + 1, topn, rank, out2_dev, stream);
+    if (!rank_dev) cudaFreeAsync(rank, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "hwer_hit_rank_metrics");
     return HWER_OK;
 }
 

@@ -87,7 +87,7 @@ struct SelExchange {
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
-                                  const SelExchange* sx, cudaStream_t stream);
+                                  unsigned int* ovf, const SelExchange* sx, cudaStream_t stream);
 
 // Where final_kernel stores a query's result when the catalogue is sharded over several GPUs: straight into the
 // exchange buffer of the GPU that owns (merges) that query, over NVLink peer stores (exchange.cu).
@@ -105,7 +105,15 @@ struct PeerDst {
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,
                          long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
-                         const PeerDst* peer, cudaStream_t stream);
+                         unsigned int* ovf, const PeerDst* peer, cudaStream_t stream);
+
+// Exhaustive exact search of ONE query at a time (the answer of last resort for a query whose candidate list cannot
+// hold everything inside the bf16 margin, e.g. tens of thousands of duplicate rows): fp64 scores of every row with
+// final_kernel's arithmetic, a stable descending radix sort, the first k.  scratch: see bruteforce_scratch_bytes.
+size_t bruteforce_scratch_bytes(long long n);
+cudaError_t launch_bruteforce_topk(const float* table, long long n, int d, const float* query, int k,
+                                   long long idx_offset, long long* out_idx, float* out_score, double* out_score64,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t stream);
 
 // Peer exchange (exchange.cu): publish "my scatter is complete" on every peer; owner-side wait + merge + delivery
 // of the merged rows to every rank; final wait + copy-out.
@@ -140,6 +148,21 @@ cudaError_t launch_pair_score(const float* table, long long n, int d, const long
 cudaError_t launch_compose_queries(const float* table, long long n, int d, const long long* anchor,
                                    const long long* pos_ptr, const long long* pos_rows, const long long* neg_ptr,
                                    const long long* neg_rows, int B, float* out, cudaStream_t stream);
+
+// unit(mean(rows of list l)) per CSR list (get_average_embeddings, hwer/recommendation_base.py:153-155)
+cudaError_t launch_average_embeddings(const float* table, long long n, int d, const long long* ptr,
+                                      const long long* rows, int L, float* out, cudaStream_t stream);
+
+// rerank.cu: score conventions + stable per-anchor ordering of the k retrieved rows, and the row gathers around them
+enum : int { kScorePair = 0, kScoreDist = 1, kScoreGiven = 2, kScoreEuclid = 3 };
+cudaError_t launch_rerank(const float* table, long long n, int d, const long long* rows, const long long* row_map,
+                          int B, int k, int conv, const long long* anchor_rows, const float* queries,
+                          const float* given, long long* out_rows, double* out_score, cudaStream_t stream);
+cudaError_t launch_map_rows(const long long* rows, long long count, const long long* row_map, long long offset,
+                            long long* out, cudaStream_t stream);
+cudaError_t launch_gather_rows(const float* table, long long n, int d, const long long* rows, long long P, float* out,
+                               cudaStream_t stream);
+cudaError_t launch_hit_rank(const float* scores, int U, int M1, int topn, int* rank, double* out2, cudaStream_t stream);
 
 cudaError_t launch_eval(const long long* topk, int U, int Kret, const long long* train_ptr,
                         const long long* train_idx, const long long* val_ptr, const long long* val_idx,

@@ -105,6 +105,23 @@ compose_queries_kernel(const float* __restrict__ table, long long n, int d, cons
     }
 }
 
+// get_average_embeddings (hwer/recommendation_base.py:153-155): unit(mean(rows)) of each CSR list, one warp each.
+__global__ void __launch_bounds__(256)
+average_embeddings_kernel(const float* __restrict__ table, long long n, int d, const long long* __restrict__ ptr,
+                          const long long* __restrict__ rows, int L, float* __restrict__ out) {
+    const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (l >= L) return;
+    float acc[kComposeMaxPerLane];
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) acc[j] = 0.f;
+    mean_unit_accumulate(table, n, d, rows, ptr[l], ptr[l + 1], 1.0f, acc);     // empty list: 0/0 = NaN like numpy
+#pragma unroll
+    for (int j = 0; j < kComposeMaxPerLane; ++j) {
+        const int c = lane_id() + 32 * j;
+        if (c < d) out[(size_t)l * d + c] = acc[j];
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Evaluation: one warp per user.
 // per_user row layout (M = 3 * n_cut + 1 doubles):
@@ -261,6 +278,14 @@ cudaError_t launch_compose_queries(const float* table, long long n, int d, const
     if (d > 32 * kComposeMaxPerLane) return cudaErrorInvalidValue;
     compose_queries_kernel<<<(B + 7) / 8, 256, 0, stream>>>(table, n, d, anchor, pos_ptr, pos_rows, neg_ptr, neg_rows, B,
                                                             out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_average_embeddings(const float* table, long long n, int d, const long long* ptr,
+                                      const long long* rows, int L, float* out, cudaStream_t stream) {
+    if (L <= 0) return cudaSuccess;
+    if (d > 32 * kComposeMaxPerLane) return cudaErrorInvalidValue;
+    average_embeddings_kernel<<<(L + 7) / 8, 256, 0, stream>>>(table, n, d, ptr, rows, L, out);
     return cudaGetLastError();
 }
 

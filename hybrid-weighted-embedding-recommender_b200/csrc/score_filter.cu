@@ -527,12 +527,15 @@ __global__ void fill_f32_kernel(float* p, long long n, float v) {
 // One instantiation per (mode, K blocks); the opt-in shared-memory ceiling is a per-function, per-process setting.
 template <int MODE, int KB>
 cudaError_t launch_tc_one(int grid, size_t smem, const CUtensorMap& tmap, const FilterParams& p, cudaStream_t stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the attribute is per device (a process may build indexes on several GPUs): remember it per device ordinal
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(score_filter_tc_kernel<MODE, KB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     score_filter_tc_kernel<MODE, KB><<<grid, kThreadsTc, smem, stream>>>(tmap, p);
     return cudaGetLastError();
@@ -617,9 +620,10 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
     long long maxb = (long long)num_sms * 8;
     int grid = (int)(blocks < maxb ? blocks : maxb);
     size_t smem = (size_t)kSimtQ * d * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(score_filter_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(smem > 48 * 1024 ? smem : 48 * 1024));
-    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {      // only widths past 1536 columns need the opt-in ceiling
+        cudaError_t e = cudaFuncSetAttribute(score_filter_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     score_filter_simt_kernel<<<grid, kSimtThreads, smem, stream>>>(table, n_items, d, queries, B, thr, cand, cnt, cap,
                                                                    row_begin, row_end);
     return cudaGetLastError();

@@ -14,6 +14,8 @@
 // One CTA per query; lists are sorted in shared memory with a bitonic network.
 #include <cstring>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -85,7 +87,8 @@ __device__ __forceinline__ void sel_publish_kth(const SelExchange& sx, long long
 __global__ void __launch_bounds__(kSelThreads)
 select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap, int K,
                       int fixed_count, const float* __restrict__ margin, float* __restrict__ thr,
-                      unsigned int* needed_cap, const __grid_constant__ SelExchange sx) {
+                      unsigned int* needed_cap, unsigned int* __restrict__ ovf,
+                      const __grid_constant__ SelExchange sx) {
     extern __shared__ unsigned long long keys[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sel_prefix, sel_remaining, kept_s, valid_s;
@@ -96,7 +99,7 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
     }
     unsigned int c_raw = fixed_count >= 0 ? (unsigned int)fixed_count : cnt[q];
     if (c_raw > cap) {
-        if (threadIdx.x == 0) atomicMax(needed_cap, c_raw);
+        if (threadIdx.x == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
         c_raw = cap;
     }
     const int c = (int)c_raw;
@@ -200,7 +203,8 @@ constexpr int kSelWarpKeys = 1024;          // keys staged per warp (8 KB); long
 __global__ void __launch_bounds__(kSelWarps * 32)
 select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap,
                            int B, int K, const float* __restrict__ margin, float* __restrict__ thr,
-                           unsigned int* needed_cap, const __grid_constant__ SelExchange sx) {
+                           unsigned int* needed_cap, unsigned int* __restrict__ ovf,
+                           const __grid_constant__ SelExchange sx) {
     __shared__ unsigned long long keys_all[kSelWarps][kSelWarpKeys];
     __shared__ unsigned int hist_all[kSelWarps][256];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -213,7 +217,7 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
     unsigned int* hist = hist_all[w];
     unsigned int c_raw = cnt[q];
     if (c_raw > cap) {
-        if (l == 0) atomicMax(needed_cap, c_raw);
+        if (l == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
         c_raw = cap;
     }
     const int c = (int)c_raw;
@@ -345,14 +349,17 @@ __global__ void __launch_bounds__(kFinalThreads, 2)      // two CTAs (32 warps) 
 final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned int cap,
              int K, const float* __restrict__ table, int d, const float* __restrict__ queries, long long idx_offset,
              long long* __restrict__ out_idx, float* __restrict__ out_score, double* __restrict__ out_score64,
-             unsigned int* needed_cap, const __grid_constant__ PeerDst peer) {
+             unsigned int* needed_cap, unsigned int* __restrict__ ovf, const __grid_constant__ PeerDst peer) {
     extern __shared__ unsigned long long sm[];
     const int q = blockIdx.x;
     unsigned int c_raw = cnt[q];
     if (c_raw > cap) {
-        if (threadIdx.x == 0) atomicMax(needed_cap, c_raw);
+        if (threadIdx.x == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
         c_raw = cap;
     }
+    // a list that overflowed in ANY round of this call may have lost a true neighbour: the whole row is marked
+    // (row -2 in column 0) so the caller can tell which queries to re-run with a larger cap / exhaustively
+    const bool overflowed = ovf[q] != 0u || cnt[q] > cap;
     const int c = (int)c_raw;
     const int P = next_pow2(c > 1 ? c : 2);
     unsigned long long* sk = sm;                                   // [P] ordered score (fp64 or fp32 image)
@@ -438,6 +445,7 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
             out_score[o] = __int_as_float(0xff800000);
             if (out_score64) out_score64[o] = -INFINITY;
         }
+        if (overflowed && i == 0) out_idx[o] = -2;
     }
 }
 
@@ -479,6 +487,52 @@ merge_kernel(const double* __restrict__ scores, const long long* __restrict__ id
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exhaustive exact search of one query: the answer of last resort (see kernels.h).  Scores every row with the same
+// fp64 arithmetic final_kernel uses for that table width (so results are bit-identical to the filtered path),
+// then a stable descending radix sort of (score image, row): equal scores stay in ascending row order.
+__global__ void __launch_bounds__(256)
+bruteforce_score_kernel(const float* __restrict__ table, long long n, int d, const float* __restrict__ qv,
+                        unsigned long long* __restrict__ keys, unsigned int* __restrict__ rows) {
+    const bool vec = (d % 128 == 0) && d <= 512 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(qv)) & 15u) == 0;
+    const long long warps = (long long)gridDim.x * 8;
+    const long long w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (vec) {
+        float4 qreg[4];
+        const int nblk = d / 128;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            qreg[b] = b < nblk ? __ldg(reinterpret_cast<const float4*>(qv) + b * 32 + lane_id()) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long r = 2 * w0; r < n; r += 2 * warps) {
+            const long long r2 = r + 1 < n ? r + 1 : r;
+            double sa, sb;
+            exact_dot2_v4(table + (size_t)r * d, table + (size_t)r2 * d, qreg, nblk, sa, sb);
+            if (lane_id() == 0) {
+                keys[r] = sa == sa ? f64_to_ordered(sa) : 0ull;
+                rows[r] = (unsigned int)r;
+                if (r + 1 < n) { keys[r + 1] = sb == sb ? f64_to_ordered(sb) : 0ull; rows[r + 1] = (unsigned int)(r + 1); }
+            }
+        }
+    } else {
+        for (long long r = w0; r < n; r += warps) {
+            const double s = exact_dot(table + (size_t)r * d, qv, d);
+            if (lane_id() == 0) { keys[r] = s == s ? f64_to_ordered(s) : 0ull; rows[r] = (unsigned int)r; }
+        }
+    }
+}
+
+__global__ void bruteforce_emit_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ rows,
+                                       int K, long long idx_offset, long long* __restrict__ out_idx,
+                                       float* __restrict__ out_score, double* __restrict__ out_score64) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const unsigned long long kk = keys[i];
+    const double s = kk ? ordered_to_f64(kk) : -INFINITY;
+    out_idx[i] = kk ? (long long)rows[i] + idx_offset : -1;
+    out_score[i] = (float)s;
+    if (out_score64) out_score64[i] = s;
+}
+
 // Raises a kernel's opt-in dynamic shared-memory ceiling (static shared memory counts against the same 227 KB).
 template <class Kern>
 cudaError_t set_smem(Kern k, size_t bytes) {
@@ -496,13 +550,13 @@ inline size_t pow2_ge(size_t v) {
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
-                                  const SelExchange* sxp, cudaStream_t stream) {
+                                  unsigned int* ovf, const SelExchange* sxp, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     SelExchange sx;
     if (sxp) sx = *sxp; else memset(&sx, 0, sizeof sx);
     if (fixed_count < 0 && B >= 128) {      // filter rounds of large batches: short lists, one warp per query
         select_compact_warp_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(
-            cand, cnt, cap, B, K, margin, thr, needed_cap, sx);
+            cand, cnt, cap, B, K, margin, thr, needed_cap, ovf, sx);
         return cudaGetLastError();
     }
     // stage only what can be there: a dense round holds fixed_count keys, a filter round at most cap
@@ -510,14 +564,15 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
     const size_t smem = (n < 1024 ? 1024 : n) * sizeof(unsigned long long);
     cudaError_t e = set_smem(select_compact_kernel, smem);
     if (e != cudaSuccess) return e;
-    select_compact_kernel<<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, fixed_count, margin, thr, needed_cap, sx);
+    select_compact_kernel<<<B, kSelThreads, smem, stream>>>(cand, cnt, cap, K, fixed_count, margin, thr, needed_cap, ovf,
+                                                            sx);
     return cudaGetLastError();
 }
 
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,
                          long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
-                         const PeerDst* peer, cudaStream_t stream) {
+                         unsigned int* ovf, const PeerDst* peer, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = pow2_ge(cap) * (sizeof(unsigned long long) + sizeof(uint32_t));
     PeerDst pd;
@@ -527,13 +582,57 @@ cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt
         e = set_smem(final_kernel<true>, smem);
         if (e != cudaSuccess) return e;
         final_kernel<true><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset, out_idx,
-                                                            out_score, out_score64, needed_cap, pd);
+                                                            out_score, out_score64, needed_cap, ovf, pd);
     } else {
         e = set_smem(final_kernel<false>, smem);
         if (e != cudaSuccess) return e;
         final_kernel<false><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
-                                                             out_idx, out_score, out_score64, needed_cap, pd);
+                                                             out_idx, out_score, out_score64, needed_cap, ovf, pd);
     }
+    return cudaGetLastError();
+}
+
+namespace {
+struct BruteLayout { size_t keys_in, keys_out, rows_in, rows_out, temp, temp_bytes, total; };
+BruteLayout brute_layout(long long n) {
+    BruteLayout L;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                              (const unsigned int*)nullptr, (unsigned int*)nullptr, (int)n);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t off = 0;
+    L.keys_in = off; off += al((size_t)n * 8);
+    L.keys_out = off; off += al((size_t)n * 8);
+    L.rows_in = off; off += al((size_t)n * 4);
+    L.rows_out = off; off += al((size_t)n * 4);
+    L.temp = off; off += al(tb);
+    L.temp_bytes = tb;
+    L.total = off;
+    return L;
+}
+}  // namespace
+
+size_t bruteforce_scratch_bytes(long long n) { return brute_layout(n).total; }
+
+cudaError_t launch_bruteforce_topk(const float* table, long long n, int d, const float* query, int k,
+                                   long long idx_offset, long long* out_idx, float* out_score, double* out_score64,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    const BruteLayout L = brute_layout(n);
+    if (scratch_bytes < L.total || n >= (1LL << 31)) return cudaErrorInvalidValue;
+    unsigned char* b = static_cast<unsigned char*>(scratch);
+    unsigned long long* keys_in = reinterpret_cast<unsigned long long*>(b + L.keys_in);
+    unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(b + L.keys_out);
+    unsigned int* rows_in = reinterpret_cast<unsigned int*>(b + L.rows_in);
+    unsigned int* rows_out = reinterpret_cast<unsigned int*>(b + L.rows_out);
+    long long blocks = (n + 15) / 16;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    bruteforce_score_kernel<<<(int)blocks, 256, 0, stream>>>(table, n, d, query, keys_in, rows_in);
+    size_t tb = L.temp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(b + L.temp, tb, keys_in, keys_out, rows_in, rows_out, (int)n,
+                                                              0, 64, stream);
+    if (e != cudaSuccess) return e;
+    bruteforce_emit_kernel<<<(k + 255) / 256, 256, 0, stream>>>(keys_out, rows_out, k, idx_offset, out_idx, out_score,
+                                                                out_score64);
     return cudaGetLastError();
 }
 

@@ -179,16 +179,39 @@ class TopKIndex:
             rc = N.lib().hwer_topk_finish(self._h, _stream(self.device), ctypes.byref(need))
         return rc, int(need.value)
 
+    MAX_CAP = 16384      # longest candidate list the selector can hold (csrc/api.cu make_schedule)
+
+    def topk_exhaustive(self, queries, k, idx_offset=0):
+        """hwer_topk_exhaustive: the same exact answer by scoring every row (slow; the path of last resort)."""
+        queries = _need(queries, torch.float32, "queries", 2)
+        B, k = queries.shape[0], int(k)
+        idx = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        score = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        s64 = torch.empty((B, k), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_topk_exhaustive(self._h, _dev_ptr(queries), B, k, int(idx_offset), _dev_ptr(idx),
+                                                 _dev_ptr(score), _dev_ptr(s64), _stream(self.device)))
+        return idx, score, s64
+
     def topk(self, queries, k, mode="exact", idx_offset=0, want_f64=False):
-        """Synchronous search with automatic retry when the candidate lists overflow (heavily tied data)."""
+        """Synchronous search.  Candidate-list overflow (heavily tied data) is retried with the capacity the kernels
+        ask for; queries that need more than the selector can hold (MAX_CAP rows inside the bf16 margin of their
+        k-th score, e.g. tens of thousands of duplicated cold-start embeddings) are answered exhaustively, so like
+        the reference's KDTree the call always returns the exact result."""
         cap = 0
         for _ in range(6):
-            idx, score, s64 = self.topk_async(queries, k, mode, idx_offset, cap, want_f64=want_f64)
+            idx, score, s64 = self.topk_async(queries, k, mode, idx_offset, cap, want_f64=True)
             rc, need = self.finish()
             if rc == N.HWER_OK:
                 return (idx, score, s64) if want_f64 else (idx, score)
             if rc != N.HWER_E_OVERFLOW:
                 N.check(rc)
+            if need > self.MAX_CAP:
+                marked = torch.nonzero(idx[:, 0] == -2).reshape(-1)          # rare path: torch glue is fine here
+                if marked.numel():
+                    e_idx, e_sc, e_s64 = self.topk_exhaustive(queries.index_select(0, marked).contiguous(), k, idx_offset)
+                    idx[marked], score[marked], s64[marked] = e_idx, e_sc, e_s64
+                return (idx, score, s64) if want_f64 else (idx, score)
             cap = need
         N.check(rc)
 
@@ -254,6 +277,88 @@ def compose_queries(table, anchor_rows, pos=None, neg=None):
                                              _dev_ptr(pp), _dev_ptr(pr), _dev_ptr(np_), _dev_ptr(nr), B, _dev_ptr(out),
                                              _stream(table.device)))
     return out
+
+
+def average_embeddings(table, ptr, rows):
+    """unit(mean(rows of each CSR list)) -- get_average_embeddings, hwer/recommendation_base.py:153-155.
+    ptr [L+1] / rows int64 CUDA tensors; row -1 = node never trained on.  Returns [L, d] fp32."""
+    table = _need(table, torch.float32, "table", 2)
+    ptr = _need(ptr, torch.int64, "ptr", 1)
+    rows = _need(rows, torch.int64, "rows", 1)
+    L = ptr.shape[0] - 1
+    out = torch.empty((L, table.shape[1]), dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_average_embeddings(_dev_ptr(table), table.shape[0], table.shape[1], _dev_ptr(ptr),
+                                                _dev_ptr(rows), L, _dev_ptr(out), _stream(table.device)))
+    return out
+
+
+def gather_rows(table, rows):
+    """get_embeddings (hwer/recommendation_base.py:146-151): table[rows], clip(table[0], 1e-6, 1e-5) for row -1."""
+    table = _need(table, torch.float32, "table", 2)
+    rows = _need(rows, torch.int64, "rows", 1)
+    out = torch.empty((rows.shape[0], table.shape[1]), dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_gather_rows(_dev_ptr(table), table.shape[0], table.shape[1], _dev_ptr(rows), rows.shape[0],
+                                         _dev_ptr(out), _stream(table.device)))
+    return out
+
+
+def map_rows(rows, row_map=None, offset=0):
+    """Local rows of a per-type index -> global rows (negative ids pass through)."""
+    rows = _need(rows, torch.int64, "rows")
+    if row_map is not None:
+        row_map = _need(row_map, torch.int64, "row_map", 1)
+    out = torch.empty_like(rows)
+    with torch.cuda.device(rows.device):
+        N.check(N.lib().hwer_map_rows(_dev_ptr(rows), rows.numel(), _dev_ptr(row_map), int(offset), _dev_ptr(out),
+                                      _stream(rows.device)))
+    return out
+
+
+_CONVENTIONS = {"pair": N.SCORE_PAIR, "dist": N.SCORE_DIST, "given": N.SCORE_GIVEN, "euclid": N.SCORE_EUCLID}
+
+
+def rerank(table, rows, convention, anchor_rows=None, queries=None, given=None, row_map=None):
+    """Scores the [B, k] retrieved rows in one of the reference's conventions and orders every anchor's list by
+    that score (stable, like Python's sorted): "pair" (anchor . row + 1) / 2, "dist" (2 - ||row - query||) / 2,
+    "given" caller-supplied scores -- all descending -- or "euclid" ||row - query|| ascending.  See hwer_rerank in
+    include/hwer_b200.h.  Returns (rows [B, k] int64, scores [B, k] float64)."""
+    table = _need(table, torch.float32, "table", 2)
+    rows = _need(rows, torch.int64, "rows", 2)
+    B, k = rows.shape
+    if anchor_rows is not None:
+        anchor_rows = _need(anchor_rows, torch.int64, "anchor_rows", 1)
+    if queries is not None:
+        queries = _need(queries, torch.float32, "queries", 2)
+        if tuple(queries.shape) != (B, table.shape[1]):
+            raise ValueError("queries must be [B, d]")
+    if given is not None:
+        given = _need(given, torch.float32, "given", 2)
+        if tuple(given.shape) != (B, k):
+            raise ValueError("given scores must be [B, k]")
+    if row_map is not None:
+        row_map = _need(row_map, torch.int64, "row_map", 1)
+    out_rows = torch.empty_like(rows)
+    out_score = torch.empty((B, k), dtype=torch.float64, device=rows.device)
+    with torch.cuda.device(table.device):
+        N.check(N.lib().hwer_rerank(_dev_ptr(table), table.shape[0], table.shape[1], _dev_ptr(rows), _dev_ptr(row_map),
+                                    B, k, _CONVENTIONS[convention], _dev_ptr(anchor_rows), _dev_ptr(queries),
+                                    _dev_ptr(given), _dev_ptr(out_rows), _dev_ptr(out_score), _stream(table.device)))
+    return out_rows, out_score
+
+
+def hit_rank_metrics(scores, topn=10, want_rank=False):
+    """HR@topn / binary NDCG@topn of the positive in column 0 of scores [U, 1 + M] (ncf_eval,
+    hwer/validation.py:82-96).  Returns a float64 tensor {hr, ndcg} (and the [U] int32 ranks)."""
+    scores = _need(scores, torch.float32, "scores", 2)
+    U, M1 = scores.shape
+    out = torch.empty(2, dtype=torch.float64, device=scores.device)
+    rank = torch.empty(U, dtype=torch.int32, device=scores.device) if want_rank else None
+    with torch.cuda.device(scores.device):
+        N.check(N.lib().hwer_hit_rank_metrics(_dev_ptr(scores), U, M1 - 1, int(topn), _dev_ptr(out), _dev_ptr(rank),
+                                              _stream(scores.device)))
+    return (out, rank) if want_rank else out
 
 
 def ncf_param_count(F, depth):

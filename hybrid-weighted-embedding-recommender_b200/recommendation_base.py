@@ -154,33 +154,26 @@ class MultiKNN:
             self._tables[nt] = sub
             self.knn[nt] = ops.TopKIndex(sub, sh, max_norm=max_norm)
 
-    def _to_global(self, node_type, local_rows):
-        off = self.offset[node_type]
-        if off is not None:
-            return torch.where(local_rows >= 0, local_rows + off, local_rows)
-        g = self.idxs_dev[node_type][local_rows.clamp(min=0)]
-        return torch.where(local_rows >= 0, g, local_rows)
-
     def query_batch(self, embeddings, node_type, k=200, mode=None, want_f64=False):
         """[B, d] query embeddings -> (global rows [B, k] int64, dot products [B, k] fp32[, fp64]) on the device,
-        ordered (score descending, row ascending)."""
+        ordered (score descending, row ascending).  A type whose rows are a range of the table gets its global
+        rows straight from the search (idx_offset); a gathered type goes through hwer_map_rows."""
         q = _as_device_table(embeddings, self.device)
         if q.dim() == 1:
             q = q[None, :]
-        res = self.knn[node_type].topk(q, k, mode or self.mode, want_f64=want_f64)
-        rows = self._to_global(node_type, res[0])
+        off = self.offset[node_type]
+        res = self.knn[node_type].topk(q, k, mode or self.mode, idx_offset=off or 0, want_f64=want_f64)
+        rows = res[0] if off is not None else ops.map_rows(res[0], self.idxs_dev[node_type])
         return (rows,) + tuple(res[1:])
 
     def query(self, embedding, node_type, k=200) -> List[Tuple[Node, float]]:
-        """hwer/recommendation_base.py:78-83: k nearest rows of `node_type` by Euclidean distance, ascending."""
+        """hwer/recommendation_base.py:78-83: k nearest rows of `node_type` by Euclidean distance, ascending
+        (distance of the fp32 rows to the embedding in float64, like KDTree64)."""
         q = _as_device_table(embedding, self.device).reshape(1, -1)
         rows, _ = self.query_batch(q, node_type, k=k)
-        rows = rows[0]
-        # Euclidean distance of the (fp32) rows to the embedding, in float64 like KDTree64
-        dist = (self.table.index_select(0, rows).double() - q.double()).norm(dim=1)
+        rows, dist = ops.rerank(self.table, rows, "euclid", queries=q)
         inv = self.nodes_to_idx.inverse
-        results = [(inv[i], dt) for i, dt in zip(rows.cpu().tolist(), dist.cpu().tolist())]
-        return list(sorted(results, key=operator.itemgetter(1), reverse=False))
+        return [(inv[i], dt) for i, dt in zip(rows[0].cpu().tolist(), dist[0].cpu().tolist()) if i >= 0]
 
 
 class RecommendationBase(metaclass=abc.ABCMeta):
@@ -246,23 +239,16 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         return self.predict_rows(self._rows_of(src), self._rows_of(dst)).cpu().numpy()
 
     def get_embeddings(self, nodes: List[Node]):
-        rows = self._rows_of(nodes)
-        emb = self.device_vectors.index_select(0, rows.clamp(min=0))
-        mask = rows < 0
-        if bool(mask.any()):
-            emb[mask] = emb[mask].clamp(1e-6, 1e-5)
-        return emb.cpu().numpy()
+        """:146-151: the nodes' rows; a node never trained on gets clip(row 0, 1e-6, 1e-5)."""
+        return ops.gather_rows(self.device_vectors, self._rows_of(nodes)).cpu().numpy()
 
     def get_average_embeddings(self, entities: List[Node]):
-        rows = self._rows_of(entities)
-        return self._average_embedding(rows).cpu().numpy()
+        """:153-155: unit(mean(rows of the entities))."""
+        return self._average_embedding(self._rows_of(entities)).cpu().numpy()
 
     def _average_embedding(self, rows: torch.Tensor) -> torch.Tensor:
-        emb = self.device_vectors.index_select(0, rows.clamp(min=0))
-        mask = rows < 0
-        if bool(mask.any()):
-            emb[mask] = emb[mask].clamp(1e-6, 1e-5)
-        return ops.unit_length(emb.mean(dim=0, keepdim=True))[0]
+        ptr = torch.tensor([0, rows.shape[0]], dtype=torch.int64, device=rows.device)
+        return ops.average_embeddings(self.device_vectors, ptr, rows)[0]
 
     def _csr_rows(self, lists):
         """Per-anchor node lists -> (ptr [B+1], rows) device CSR for ops.compose_queries."""
@@ -292,15 +278,13 @@ class RecommendationBase(metaclass=abc.ABCMeta):
 
     def find_closest_neighbours(self, node_type: str, anchor: Node, positive: List[Node] = None,
                                 negative: List[Node] = None, k=200) -> List[Tuple[Node, float]]:
+        """:157-174 (and the GcnNCF override, hwer/gcn_ncf.py:363-387, through `_batch_scores`): one anchor is a
+        batch of one -- search, score convention and ordering all run in the same kernels as the batched call."""
         self._check_query(node_type, anchor)
-        embedding = self._query_embedding(anchor, positive, negative)
-        rows, _ = self.knn.query_batch(embedding[None, :], node_type, k=k)
-        rows = rows[0]
-        anchor_rows = torch.full_like(rows, self.nodes_to_idx[anchor])
-        scores = self.predict_rows(anchor_rows, rows).cpu().tolist()                  # :172
-        inv = self.nodes_to_idx.inverse
-        nodes = [inv[i] for i in rows.cpu().tolist()]
-        return list(sorted(zip(nodes, scores), key=operator.itemgetter(1), reverse=True))   # :173
+        rows, scores = self.find_closest_neighbours_batch(node_type, [anchor], k=k,
+                                                          positive=[positive] if positive else None,
+                                                          negative=[negative] if negative else None)
+        return self.rows_to_nodes(rows, scores)[0]
 
     def find_items_for_user(self, user: Node, k=200, positive: List[Node] = None, negative: List[Node] = None,
                             node_type: str = "item") -> List[Tuple[Node, float]]:
@@ -313,21 +297,17 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         reference, the anchor itself is returned first."""
         return self.find_closest_neighbours(item.node_type, item, positive, negative, k)
 
-    def _batch_scores(self, anchor_rows, rows, dots):
-        """Final score convention of the base class: (anchor . node + 1) / 2, each row sorted descending."""
-        B, k = rows.shape
-        s = self.predict_rows(anchor_rows[:, None].expand(B, k).reshape(-1).contiguous(),
-                              rows.reshape(-1).contiguous()).reshape(B, k)
-        s = torch.where(rows >= 0, s, torch.full_like(s, float("-inf")))
-        s, order = torch.sort(s, dim=1, descending=True, stable=True)
-        return torch.gather(rows, 1, order), s
+    def _batch_scores(self, anchor_rows, queries, rows):
+        """Final score convention of the base class (:172-174): (anchor . node + 1) / 2 of the table's fp32 rows --
+        NOT the composed query's score -- each anchor's list sorted descending (stable)."""
+        return ops.rerank(self.device_vectors, rows, "pair", anchor_rows=anchor_rows)
 
     def find_closest_neighbours_batch(self, node_type: str, anchors: List[Node], k=200,
                                       positive: List[List[Node]] = None, negative: List[List[Node]] = None
                                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """One search for all anchors (the loop of validation.model_get_topk_knn, hwer/validation.py:30-35).
-        Returns device tensors (global rows [B, k], scores [B, k]) in the same order and score convention as
-        find_closest_neighbours(node_type, anchor, positive[i], negative[i], k) called per anchor."""
+        Returns device tensors (global rows [B, k] int64, scores [B, k] float64) in the same order and score
+        convention as find_closest_neighbours(node_type, anchor, positive[i], negative[i], k) called per anchor."""
         assert self.fit_done
         assert node_type in self.node_types and node_type in self.knn.knn
         for a in anchors:
@@ -335,8 +315,8 @@ class RecommendationBase(metaclass=abc.ABCMeta):
                 raise NodeNotFoundException("Node = %s, was not provided in training" % a)
         anchor_rows = self._rows_of(anchors)
         queries = self._query_embeddings(anchors, positive, negative)
-        rows, dots = self.knn.query_batch(queries, node_type, k=k)
-        return self._batch_scores(anchor_rows, rows, dots)
+        rows, _ = self.knn.query_batch(queries, node_type, k=k)
+        return self._batch_scores(anchor_rows, queries, rows)
 
     def rows_to_nodes(self, rows: torch.Tensor, scores: torch.Tensor) -> List[List[Tuple[Node, float]]]:
         inv = self.nodes_to_idx.inverse

@@ -123,33 +123,14 @@ class GcnNCF(RecommendationBase):
         self.fit_done = True
         return self.vectors
 
-    def find_closest_neighbours(self, node_type: str, anchor: Node, positive: List[Node] = None,
-                                negative: List[Node] = None, k=200) -> List[Tuple[Node, float]]:
-        self._check_query(node_type, anchor)
-        embedding = self._query_embedding(anchor, positive, negative)
-        node_dist_list = self.knn.query(embedding, node_type, k=k)
-        nodes, dist = zip(*node_dist_list)
-        if self.ncf_enabled:                                                          # gcn_ncf.py:384-386
-            scores = self.predict([(anchor, node) for node in nodes])
-            return list(sorted(zip(nodes, scores), key=operator.itemgetter(1), reverse=True))
-        dist = (-1 * np.array(dist) + 2) / 2                                          # gcn_ncf.py:381
-        return list(sorted(zip(nodes, dist), key=operator.itemgetter(1), reverse=True))
-
-    def _batch_scores(self, anchor_rows, rows, dots):
+    def _batch_scores(self, anchor_rows, queries, rows):
         if self.ncf_enabled:
-            # one NCF pass over all B * k (anchor, candidate) pairs, then the per-anchor descending sort of :386
+            # gcn_ncf.py:384-386: one NCF pass over all B * k (anchor, candidate) pairs, then the per-anchor
+            # descending sort
             B, k = rows.shape
-            s = self.predict_rows(anchor_rows[:, None].expand(B, k).reshape(-1).contiguous(),
-                                  rows.clamp(min=-1).reshape(-1).contiguous()).reshape(B, k)
-            s = torch.where(rows >= 0, s, torch.full_like(s, float("-inf")))
-            s, order = torch.sort(s, dim=1, descending=True, stable=True)
-            return torch.gather(rows, 1, order), s
-        # (2 - ||q - x||) / 2 with q the unit anchor row: distance from the fp64 difference like KDTree64
-        B, k = rows.shape
-        q = ops.unit_length(self.device_vectors.index_select(0, anchor_rows)).double()
-        x = self.device_vectors.index_select(0, rows.clamp(min=0).reshape(-1)).reshape(B, k, -1).double()
-        dist = (x - q[:, None, :]).norm(dim=2)
-        s = ((2.0 - dist) / 2.0)
-        s = torch.where(rows >= 0, s, torch.full_like(s, float("-inf")))
-        s, order = torch.sort(s, dim=1, descending=True, stable=True)
-        return torch.gather(rows, 1, order), s
+            given = self.predict_rows(anchor_rows[:, None].expand(B, k).reshape(-1).contiguous(),
+                                      rows.reshape(-1)).reshape(B, k)
+            return ops.rerank(self.device_vectors, rows, "given", given=given)
+        # gcn_ncf.py:378-383: (2 - dist) / 2 with dist = KDTree64's distance of the row to the COMPOSED embedding
+        # (anchor +- positive / negative means, :369-376), not to the anchor's own row
+        return ops.rerank(self.device_vectors, rows, "dist", queries=queries)

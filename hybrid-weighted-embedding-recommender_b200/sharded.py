@@ -123,14 +123,16 @@ class ShardedTopK:
         self.group = group
         self.row_offset = int(row_offset)
         self.rows_max = int(local_table.shape[0])
+        self.rows_min = self.rows_max        # smallest shard over all ranks: every rank must pick the same exchange path
         if dist.is_initialized() and dist.get_world_size(group) > 1 and local_table.is_cuda:
             # the admission margin scales with the largest row norm of the WHOLE catalogue, and all ranks walk the
             # round schedule of the largest shard (hwer_exchange_configure): agree on both once
             if max_norm is None:
                 max_norm = ops.norm_stats(local_table)[4]
-            t = torch.tensor([float(max_norm), float(self.rows_max)], dtype=torch.float64, device=local_table.device)
+            t = torch.tensor([float(max_norm), float(self.rows_max), -float(self.rows_max)], dtype=torch.float64,
+                             device=local_table.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            max_norm, self.rows_max = float(t[0].item()), int(t[1].item())
+            max_norm, self.rows_max, self.rows_min = float(t[0].item()), int(t[1].item()), int(-t[2].item())
         self.index = ops.TopKIndex(local_table, shadow, max_norm=max_norm)
         self.exchange = exchange
         self.share_thresholds = bool(share_thresholds)
@@ -159,7 +161,7 @@ class ShardedTopK:
     def topk(self, queries, k, mode="exact"):
         k = int(k)
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
-        if multi and self.exchange in ("auto", "p2p") and self.index.n >= k and queries.is_cuda:
+        if multi and self.exchange in ("auto", "p2p") and self.rows_min >= k and queries.is_cuda:
             cap = 0
             for _ in range(6):
                 idx, score, _ = self.topk_p2p_async(queries, k, mode, cap=cap)

@@ -38,47 +38,88 @@ def model_get_topk_gpu(model: RecommendationBase, anchors: List[Node], node_type
 model_get_topk = model_get_topk_gpu
 
 
-def _csr(lists, device):
-    ptr = np.zeros(len(lists) + 1, dtype=np.int64)
-    for i, l in enumerate(lists):
-        ptr[i + 1] = ptr[i] + len(l)
-    flat = np.fromiter((x for l in lists for x in l), dtype=np.int64, count=int(ptr[-1]))
-    return torch.from_numpy(ptr).to(device), torch.from_numpy(flat).to(device)
+def _edge_arrays(model, edges):
+    """(src row, dst row, weight) numpy arrays of an edge list (-1 = node unknown to the model) and the dst nodes.
+    The one per-edge Python pass of the evaluation; everything after it is array work."""
+    n2i = model.nodes_to_idx
+    m = len(edges)
+    src = np.empty(m, dtype=np.int64)
+    dst = np.empty(m, dtype=np.int64)
+    w = np.empty(m, dtype=np.float64)
+    dst_nodes = [None] * m
+    for j, (u, i, r) in enumerate(edges):
+        src[j] = n2i.get(u, -1)
+        dst[j] = n2i.get(i, -1)
+        w[j] = r
+        dst_nodes[j] = i
+    return src, dst, w, dst_nodes
+
+
+def _csr_from_sorted(owner, n_owners):
+    """ptr [n_owners + 1] of entries already grouped by ascending `owner`."""
+    counts = np.bincount(owner, minlength=n_owners) if owner.size else np.zeros(n_owners, dtype=np.int64)
+    ptr = np.zeros(n_owners + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    return ptr
 
 
 def ranking_metrics(model: RecommendationBase, users: List[Node], topk_rows: torch.Tensor, train_edges, validation_edges,
                     node_type: NodeType, cutoffs=(10, 20, 50, 100)):
     """Device evaluation of `topk_rows` ([U, k] global rows in rank order for `users`).  Returns a dict with
-    recall@c / ndcg@c / ndcg_b@c for every cutoff, mrr, diversity and the number of validation users."""
+    recall@c / ndcg@c / ndcg_b@c for every cutoff, mrr, diversity and the number of validation users.
+    Host side: one pass over the edges to look their nodes up, then numpy builds the two CSR structures
+    hwer_eval_metrics reads (train items per user ascending; validation items per user by relevance descending,
+    the dict semantics of validation.py:158-161: per (user, item) the last rating wins)."""
     dev = topk_rows.device
-    local = {int(g): i for i, g in enumerate(model.knn.idxs[node_type])}     # global row -> item id within type
-    uidx = {u: i for i, u in enumerate(users)}
-    n2i = model.nodes_to_idx
-    train = [set() for _ in users]
-    for u, i, r in train_edges:
-        if u in uidx and i in n2i and n2i[i] in local:
-            train[uidx[u]].add(local[n2i[i]])
-    val = [dict() for _ in users]
-    for u, i, r in validation_edges:
-        if u in uidx:
-            # an item outside the index can never be retrieved but still counts as a true item: id past the table
-            item = local[n2i[i]] if (i in n2i and n2i[i] in local) else len(local) + len(val[uidx[u]])
-            val[uidx[u]][item] = float(r)     # dict semantics of validation.py:160 (last rating wins)
-    val_sorted = [sorted(v.items(), key=lambda x: -x[1]) for v in val]
-    train_ptr, train_idx = _csr([sorted(t) for t in train], dev)
-    val_ptr, val_idx = _csr([[i for i, r in v] for v in val_sorted], dev)
-    val_rel = torch.tensor([r for v in val_sorted for i, r in v], dtype=torch.float32, device=dev)
+    n_rows = len(model.nodes_to_idx)
+    type_rows = model.knn.idxs[node_type]
+    n_local = int(type_rows.shape[0])
+    local_of = np.full(n_rows + 1, -1, dtype=np.int64)         # global row -> id within the type; [-1] stays -1
+    local_of[type_rows] = np.arange(n_local, dtype=np.int64)
+    user_rows = np.fromiter((model.nodes_to_idx[u] for u in users), dtype=np.int64, count=len(users))
+    upos = np.full(n_rows + 1, -1, dtype=np.int64)             # global row -> position in `users`
+    upos[user_rows] = np.arange(len(users), dtype=np.int64)
+    U = len(users)
+
+    # training items per user: unique (user, item) pairs, ascending
+    t_src, t_dst, _, _ = _edge_arrays(model, train_edges)
+    tu, ti = upos[t_src], local_of[t_dst]
+    ok = (tu >= 0) & (ti >= 0)
+    tkey = np.unique(tu[ok] * max(n_local, 1) + ti[ok])
+    train_ptr = _csr_from_sorted(tkey // max(n_local, 1), U)
+    train_idx = tkey % max(n_local, 1)
+
+    # validation items per user
+    v_src, v_dst, v_w, v_nodes = _edge_arrays(model, validation_edges)
+    vu, vi = upos[v_src], local_of[v_dst]
+    # an item outside the index can never be retrieved but still counts as a true item: ids past the table, one
+    # per distinct node
+    extra = {}
+    for j in np.flatnonzero((vu >= 0) & (vi < 0)):
+        vi[j] = n_local + extra.setdefault(v_nodes[j], len(extra))
+    ok = vu >= 0
+    vu, vi, vw = vu[ok], vi[ok], v_w[ok]
+    span = n_local + len(extra) + 1
+    vkey = vu * span + vi
+    uniq, first = np.unique(vkey, return_index=True)                      # first time the pair appears
+    _, last_rev = np.unique(vkey[::-1], return_index=True)                # last time: its rating wins
+    rel = vw[vkey.shape[0] - 1 - last_rev] if vkey.size else vw
+    order = np.lexsort((first, -rel, uniq // span))                       # by user, relevance desc, insertion order
+    val_ptr = _csr_from_sorted((uniq // span)[order], U)
+    val_idx = (uniq % span)[order]
+    val_rel = rel[order].astype(np.float32)
+
     # global rows -> ids within the type
     off = model.knn.offset[node_type]
     if off is not None:
-        items = torch.where(topk_rows >= 0, topk_rows - off, topk_rows)
+        items = ops.map_rows(topk_rows.contiguous(), None, -off)
     else:
-        lut = torch.full((len(n2i),), -1, dtype=torch.int64, device=dev)
-        lut[model.knn.idxs_dev[node_type]] = torch.arange(len(local), device=dev)
-        items = torch.where(topk_rows >= 0, lut[topk_rows.clamp(min=0)], topk_rows)
+        lut = torch.from_numpy(local_of[:-1].copy()).to(dev)
+        items = ops.map_rows(topk_rows.contiguous(), lut)
     cutoffs = sorted(cutoffs)
-    out = ops.eval_metrics(items.contiguous(), train_ptr, train_idx, val_ptr, val_idx, val_rel, cutoffs,
-                           len(local)).cpu().tolist()
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = ops.eval_metrics(items, to_dev(train_ptr), to_dev(train_idx), to_dev(val_ptr), to_dev(val_idx),
+                           to_dev(val_rel), cutoffs, max(n_local, 1)).cpu().tolist()
     res = {}
     for j, c in enumerate(cutoffs):
         res["recall@%d" % c], res["ndcg@%d" % c], res["ndcg_b@%d" % c] = out[3 * j], out[3 * j + 1], out[3 * j + 2]
@@ -116,9 +157,11 @@ def _sample_negatives(validation_edges, interactions, ordered_items):
     return out
 
 
-def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edges: List[Edge], item_list: List[Node]):
-    """hwer/validation.py:68-97: per validation user 1 positive + 100 sampled negatives, scored by the model,
-    HR@10 and binary NDCG@10 of the positive's rank.  All 101 x users pairs are scored in one device call."""
+def ncf_eval_scores(model: RecommendationBase, train_edges: List[Edge], validation_edges: List[Edge],
+                    item_list: List[Node]):
+    """The scored candidate lists of ncf_eval (hwer/validation.py:68-84): [U, 101] scores, column 0 = the user's
+    positive, columns 1..100 = the sampled negatives, all U x 101 pairs scored in one device call.
+    None if there is no validation edge."""
     interactions = defaultdict(set)
     for u, i, _ in train_edges:
         interactions[u].add(i)
@@ -127,7 +170,7 @@ def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edge
     ordered_items = sorted(set(item_list), key=repr)
     picks = _sample_negatives(validation_edges, interactions, ordered_items)
     if not picks:
-        return {"ncf_hr": float("nan"), "ncf_ndcg": float("nan")}
+        return None
     users = list(picks.keys())
     item_rows = model._rows_of(ordered_items)                                   # rows of the candidate items, once
     user_rows = model._rows_of(users)
@@ -135,24 +178,54 @@ def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edge
     neg_pos = torch.from_numpy(np.stack([picks[u][1] for u in users])).to(item_rows.device)     # [U, 100]
     dst = torch.cat([pos_rows[:, None], item_rows[neg_pos]], dim=1).reshape(-1).contiguous()   # positive first
     src = user_rows[:, None].expand(len(users), 101).reshape(-1).contiguous()
-    s = model.predict_rows(src, dst).reshape(len(users), 101)
-    # stable descending sort keeps the positive (column 0) ahead of equal-scored negatives (validation.py:85)
-    rank = (s[:, 1:] > s[:, :1]).sum(dim=1)
-    hit = rank < 10
-    ndcg = torch.where(hit, 1.0 / torch.log2(rank.double() + 2.0) / (1.0 + 1e-8), torch.zeros_like(rank, dtype=torch.float64))
-    return {"ncf_hr": float(hit.double().mean().item()), "ncf_ndcg": float(ndcg.mean().item())}
+    return model.predict_rows(src, dst).float().reshape(len(users), 101).contiguous()
+
+
+def ncf_eval(model: RecommendationBase, train_edges: List[Edge], validation_edges: List[Edge], item_list: List[Node]):
+    """hwer/validation.py:68-97: per validation user 1 positive + 100 sampled negatives, scored by the model,
+    HR@10 and binary NDCG@10 of the positive's rank.  The rank of the positive is the number of negatives scored
+    strictly higher (the reference's stable descending sort keeps the positive, listed first, ahead of equal
+    scores, :82-85); ranks, HR@10 and NDCG@10 are computed by hwer_hit_rank_metrics on the device."""
+    s = ncf_eval_scores(model, train_edges, validation_edges, item_list)
+    if s is None:
+        return {"ncf_hr": float("nan"), "ncf_ndcg": float("nan")}
+    hr, ndcg = ops.hit_rank_metrics(s, topn=10).tolist()
+    return {"ncf_hr": hr, "ncf_ndcg": ndcg}
+
+
+def _rows_from_predictions(model, users, predictions, device):
+    """Dict[Node, List[(Node, score)]] (what a `get_topk` hook returns, validation.py:30-35) -> [U, kmax] global rows
+    in descending score order (stable, validation.py:134-135), padded with -1."""
+    n2i = model.nodes_to_idx
+    lists = []
+    for u in users:
+        p = sorted(predictions.get(u, []), key=lambda x: x[1], reverse=True)
+        lists.append([n2i.get(n, -1) for n, _ in p])
+    kmax = max([len(l) for l in lists] + [1])
+    rows = np.full((len(users), kmax), -1, dtype=np.int64)
+    for j, l in enumerate(lists):
+        rows[j, :len(l)] = l
+    return torch.from_numpy(rows).to(device)
 
 
 def extraction_efficiency(model, train_edges: List[Edge], validation_edges: List[Edge], get_topk=None,
                           node_type: NodeType = "item", k: int = 200):
+    """hwer/validation.py:100-187.  `get_topk(model, anchors, node_type) -> Dict[Node, List[(Node, score)]]` is the
+    reference's retrieval hook (:100,111).  None or this module's own `model_get_topk` take the tensor path (one
+    batched search, no Python tuples); any other callable is called exactly as the reference calls it and its
+    lists are evaluated."""
     train_users = list(set([u for u, i, r in train_edges]))
     validation_users = list(set([u for u, i, r in validation_edges]))
     all_users = list(set(train_users + validation_users))
     all_items = list(set([i for u, i, r in validation_edges] + [i for u, i, r in train_edges]))
     all_items = [x for x in all_items if x.node_type == node_type]
     s = time.time()
-    rows, scores = model.find_closest_neighbours_batch(node_type, all_users, k=k)
-    torch.cuda.synchronize()
+    if get_topk is None or get_topk is model_get_topk_gpu:
+        rows, scores = model.find_closest_neighbours_batch(node_type, all_users, k=k)
+        torch.cuda.synchronize()
+    else:
+        predictions = get_topk(model, all_users, node_type)
+        rows, scores = _rows_from_predictions(model, all_users, predictions, model.device_vectors.device), None
     pred_time = time.time() - s
     m = ranking_metrics(model, all_users, rows, train_edges, validation_edges, node_type)
     ncf_metrics = ncf_eval(model, train_edges, validation_edges, all_items)

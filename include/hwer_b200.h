@@ -92,8 +92,19 @@ int hwer_index_destroy(hwer_index_t* index);
 int hwer_topk(hwer_index_t* index, const float* queries_dev, int32_t B, int32_t k, int32_t mode, uint32_t cap,
               int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev,
               void* stream);
-/* Synchronises `stream` and reports candidate-list overflow of the topk calls enqueued since the last finish. */
+/* Synchronises `stream` and reports candidate-list overflow of the topk calls enqueued since the last finish.
+ * On HWER_E_OVERFLOW the outputs of the queries that did NOT overflow are valid; a query that did carries row -2
+ * in column 0 of out_idx_dev.  Re-run those (or everything) with cap >= *needed_cap; a list is at most 16384
+ * entries long, so when *needed_cap exceeds that (tens of thousands of rows inside the bf16 margin of the k-th
+ * score: duplicated or default cold-start embeddings) answer the marked queries with hwer_topk_exhaustive. */
 int hwer_topk_finish(hwer_index_t* index, void* stream, uint32_t* needed_cap);
+
+/* The same exact answer (same fp64 scores, same (score desc, row asc) order) by exhaustive search: every row of
+ * the index is scored in fp64 and a stable radix sort keeps the first k -- about a millisecond per million rows and
+ * query, 24 bytes of scratch per row.  The path of last resort for queries hwer_topk cannot hold in its candidate
+ * lists; like sklearn's KDTree (hwer/recommendation_base.py:79) it always answers. */
+int hwer_topk_exhaustive(hwer_index_t* index, const float* queries_dev, int32_t B, int32_t k, int64_t idx_offset,
+                         int64_t* out_idx_dev, float* out_score_dev, double* out_score64_dev, void* stream);
 
 /* Measurement aid: when enabled, every score-filter launch of hwer_topk (with the spill-extract kernel that rides
  * behind it) is bracketed by CUDA events on the
@@ -168,6 +179,52 @@ int hwer_pair_score(const float* table_dev, int64_t n, int32_t d, const int64_t*
 int hwer_compose_queries(const float* table_dev, int64_t n, int32_t d, const int64_t* anchor_rows_dev,
                          const int64_t* pos_ptr_dev, const int64_t* pos_rows_dev, const int64_t* neg_ptr_dev,
                          const int64_t* neg_rows_dev, int32_t B, float* out_dev, void* stream);
+
+/* unit(mean(rows of list l)) for L CSR lists of row ids (ptr [L+1], rows); ids outside [0, n) are nodes never
+ * trained on: clip(row 0, 1e-6, 1e-5).  An empty list yields NaN like numpy.  d <= 1024.
+ * Replaces: RecommendationBase.get_average_embeddings, hwer/recommendation_base.py:153-155. */
+int hwer_average_embeddings(const float* table_dev, int64_t n, int32_t d, const int64_t* ptr_dev,
+                            const int64_t* rows_dev, int32_t L, float* out_dev, void* stream);
+
+/* out[p] = table[rows[p]], or clip(table[0], 1e-6, 1e-5) for a row id outside [0, n).
+ * Replaces: RecommendationBase.get_embeddings, hwer/recommendation_base.py:146-151. */
+int hwer_gather_rows(const float* table_dev, int64_t n, int32_t d, const int64_t* rows_dev, int64_t P, float* out_dev,
+                     void* stream);
+
+/* Rows local to a per-type index -> global rows: out = row_map ? row_map[row] : row + offset; negative ids
+ * (missing results) pass through.  Replaces: the bidict lookup of MultiKNN.query, hwer/recommendation_base.py:80. */
+int hwer_map_rows(const int64_t* rows_dev, int64_t count, const int64_t* row_map_dev, int64_t offset,
+                  int64_t* out_dev, void* stream);
+
+/* The step every find_closest_neighbours variant ends with: score the k retrieved rows of each of B anchors in
+ * the caller's convention and order each anchor's list by that score with a STABLE sort (equal scores keep the
+ * order of `rows_dev`, as Python's sorted() does), all in one launch.
+ *   HWER_SCORE_PAIR    (table[anchor] . table[row] + 1) / 2 in fp32, descending  -- RecommendationBase.
+ *                      find_closest_neighbours' rescoring through predict, hwer/recommendation_base.py:172-174
+ *   HWER_SCORE_DIST    (2 - ||table[row] - query||) / 2 in fp64, descending      -- GcnNCF.find_closest_neighbours,
+ *                      cosine branch, hwer/gcn_ncf.py:378-383 (query = the composed embedding of :369-376)
+ *   HWER_SCORE_GIVEN   given_dev[B, k] (e.g. hwer_ncf_score output), descending  -- NCF branch, hwer/gcn_ncf.py:384-386
+ *   HWER_SCORE_EUCLID  ||table[row] - query|| in fp64, ASCENDING                 -- MultiKNN.query,
+ *                      hwer/recommendation_base.py:79-82
+ * rows_dev [B, k]: rows as returned by hwer_topk (-1 = none; these sort last and come out as row -1, score -inf,
+ * +inf for EUCLID).  row_map_dev (may be NULL): rows are local to a gathered per-type index and row_map[row] is
+ * the row of table_dev; out_rows_dev then holds the mapped rows.  anchor_rows_dev [B] (PAIR), queries_dev [B, d]
+ * (DIST, EUCLID), given_dev [B, k] (GIVEN): the others may be NULL.  out_score_dev [B, k] doubles.  k <= 8192. */
+#define HWER_SCORE_PAIR 0
+#define HWER_SCORE_DIST 1
+#define HWER_SCORE_GIVEN 2
+#define HWER_SCORE_EUCLID 3
+int hwer_rerank(const float* table_dev, int64_t n, int32_t d, const int64_t* rows_dev, const int64_t* row_map_dev,
+                int32_t B, int32_t k, int32_t convention, const int64_t* anchor_rows_dev, const float* queries_dev,
+                const float* given_dev, int64_t* out_rows_dev, double* out_score_dev, void* stream);
+
+/* HR@topn and binary NDCG@topn of one positive among M sampled negatives per user.
+ * Replaces: the per-user sort / top-10 / binary_ndcg_v2 loop of validation.ncf_eval, hwer/validation.py:82-96.
+ * scores_dev [U, 1 + M] fp32, column 0 = the positive (equal-scored negatives rank behind it, as the reference's
+ * stable sort leaves them).  out2_dev = {mean(rank < topn), mean(rank < topn ? 1 / log2(rank + 2) / (1 + 1e-8) : 0)};
+ * rank_dev (NULL to skip) receives the [U] ranks (number of negatives scored strictly higher). */
+int hwer_hit_rank_metrics(const float* scores_dev, int32_t U, int32_t M, int32_t topn, double* out2_dev,
+                          int32_t* rank_dev, void* stream);
 
 /* NCF re-rank: out[p] = sigmoid(w_out . MLP([h[src[p]] || h[dst[p]]]) + b_out), fp32.
  * Replaces: NCF.forward, hwer/ncf.py:7-27, as driven by GcnNCF.predict, hwer/gcn_ncf.py:336-361, and by the NCF

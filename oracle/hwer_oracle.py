@@ -384,3 +384,31 @@ def link_prediction_accuracy(model, nodes, train_edges, validation_edges, rng):
         out["lp_%s_ap" % name], out["lp_%s_precision" % name] = ap, p
         out["lp_%s_recall" % name], out["lp_%s_accuracy" % name] = r, a
     return out
+
+
+def ncf_eval(model, train_edges, validation_edges, item_list, rng):
+    """hwer/validation.py:68-97: per validation edge 1 positive + 100 negatives drawn with random.sample from the
+    items the user never touched, scored by model.predict, stable descending sort, top 10 -> HR@10 and
+    binary_ndcg_v2([positive], top10), averaged over users (one entry per user: the last edge wins, :79-81).
+    Python >= 3.11 refuses to sample from a set, so the pool is given the one deterministic order a set of Nodes
+    has -- sorted by repr -- exactly what oracle/ref_shim.py does to run the unmodified reference here.
+    `rng`: the `random` module or a random.Random.  Returns (ncf_hr, ncf_ndcg, {user: rank of the positive})."""
+    item_list = set(item_list)
+    interactions = defaultdict(set)
+    for u, i, _ in train_edges:
+        interactions[u].add(i)
+    for u, i, _ in validation_edges:
+        interactions[u].add(i)
+    user_test_item, actual = {}, {}
+    for u, i, _ in validation_edges:
+        user_test_item[u] = [i, *rng.sample(sorted(item_list - interactions[u], key=repr), 100)]
+        actual[u] = i
+    top10, ranks = {}, {}
+    for u, items in user_test_item.items():
+        it = list(zip(items, model.predict([(u, i) for i in items])))
+        it = list(sorted(it, key=operator.itemgetter(1), reverse=True))
+        ranks[u] = [x for x, _ in it].index(items[0])
+        top10[u], _ = zip(*it[:10])
+    hr = [actual[u] in top10[u] for u in actual]
+    nd = [binary_ndcg_v2([actual[u]], top10[u]) for u in actual]
+    return float(np.mean(hr)), float(np.mean(nd)), ranks

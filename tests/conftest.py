@@ -81,3 +81,13 @@ def golden_c2():
 @pytest.fixture(scope="session")
 def golden_c3():
     return np.load(os.path.join(GOLDEN, "reference_c3.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_r2():
+    return np.load(os.path.join(GOLDEN, "reference_r2.npz"))
+
+
+def posneg_lists(u, n_items):
+    """Positive / negative item ids of anchor user u in reference_c1.npz's and reference_r2.npz's pos/neg cases."""
+    return [(u * 3 + j) % n_items for j in range(3)], [(u * 5 + j + 1) % n_items for j in range(2)]

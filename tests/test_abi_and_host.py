@@ -184,9 +184,15 @@ def test_ncf_eval_host_logic_with_a_stub_model():
     train = [hw.Edge(u, items[100 + j], 1.0) for j, u in enumerate(users)]
     val = [hw.Edge(u, items[j], 1.0) for j, u in enumerate(users)]
     random.seed(0)
-    out = hw.validation.ncf_eval(Stub(), train, val, items)
-    assert abs(out["ncf_hr"] - 3 / 5) < 1e-12                       # users 0, 2, 4 rank their positive first
-    assert abs(out["ncf_ndcg"] - (3 / 5) * (1.0 / math.log2(2.0)) / (1.0 + 1e-8)) < 1e-9
+    s = hw.validation.ncf_eval_scores(Stub(), train, val, items).numpy()
+    assert s.shape == (5, 101)
+    np.testing.assert_array_equal(s[:, 0], np.float32([0.9, 0.0, 0.9, 0.0, 0.9]))    # the positive is column 0
+    assert (s[:, 1:] == 0.5).all()                                                    # 100 negatives, never the positive
+    rank = (s[:, 1:] > s[:, :1]).sum(1)                 # what hwer_hit_rank_metrics counts on the device
+    assert list(rank) == [0, 100, 0, 100, 0]
+    with pytest.raises(RuntimeError):                   # the metric arithmetic has no CPU path
+        hw.validation.ncf_eval(Stub(), train, val, items)
+    assert hw.validation.ncf_eval_scores(Stub(), train, [], items) is None
 
 
 def test_node_hash_is_recomputed_after_pickling_into_another_process():

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import hwer_oracle as O
-from conftest import synthetic_case, synthetic_edges
+from conftest import posneg_lists, synthetic_case, synthetic_edges
 
 pytestmark = pytest.mark.gpu
 
@@ -629,6 +629,204 @@ def test_gcn_ncf_rerank_matches_reference(hw, golden_ncf):
     np.testing.assert_allclose(sc.cpu().numpy(), g["fcn_score"], rtol=0, atol=1e-5)
 
 
+def test_more_ties_than_the_selector_holds_falls_back_to_exhaustive_search(hw):
+    """more than 16384 rows inside the bf16 margin of the k-th score (duplicated cold-start embeddings)
+    used to raise; the reference's KDTree always answers.  Now the marked queries are answered exhaustively --
+    same rows (ascending among exact duplicates), same fp64 scores -- while the other queries keep their result."""
+    n, d, k = 60000, 128, 100
+    t_np, _ = unit_table(n, d, 81)
+    q_np, _ = unit_table(6, d, 82)
+    dup = np.arange(5000, 5000 + 20000)
+    t_np[dup] = q_np[2]                                       # 20,000 copies of query 2
+    t = torch.from_numpy(t_np).cuda()
+    q = torch.from_numpy(q_np).cuda()
+    index = hw.ops.TopKIndex(t)
+    idx, sc, s64 = index.topk(q, k, want_f64=True)
+    ref_idx, ref_sc = O.exact_topk(t_np, q_np, k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)
+    assert idx[2].cpu().tolist() == list(range(5000, 5000 + k))
+    np.testing.assert_allclose(s64.cpu().numpy(), ref_sc, rtol=0, atol=1e-6)
+    # the exhaustive path alone: bit-identical to the filtered path on ordinary queries
+    e_idx, e_sc, e_s64 = index.topk_exhaustive(q[[0, 1, 3]].contiguous(), k)
+    assert torch.equal(e_idx, idx[[0, 1, 3]]) and torch.equal(e_s64, s64[[0, 1, 3]])
+    t2_np, t2 = unit_table(3000, 100, 83)                     # scalar-dot width (d % 128 != 0), k close to n
+    q2_np, q2 = unit_table(4, 100, 84)
+    i2 = hw.ops.TopKIndex(t2)
+    a = i2.topk(q2, 1000, want_f64=True)
+    b = i2.topk_exhaustive(q2, 1000, idx_offset=7)
+    assert torch.equal(a[0] + 7, b[0]) and torch.equal(a[2], b[2])
+
+
+# ----------------------------------------------------------------------------- round 2: reference_r2.npz
+def test_gcn_posneg_single_and_batch_match_reference(c1_model, golden_r2, hw):
+    """GcnNCF.find_closest_neighbours with positive / negative lists (hwer/gcn_ncf.py:363-383): (2 - dist) / 2 with
+    dist measured to the COMPOSED embedding -- per anchor and batched, against the reference's own outputs."""
+    m, g, k = c1_model["gcn"], c1_model["g"], c1_model["k"]
+    users, items = c1_model["users"], c1_model["items"]
+    anchors = [users[int(u)] for u in g["user_anchors"][:16]]
+    pn = [posneg_lists(int(u), len(items)) for u in g["user_anchors"][:16]]
+    pos = [[items[t] for t in p] for p, n in pn]
+    neg = [[items[t] for t in n] for p, n in pn]
+    for j, a in enumerate(anchors):
+        idx, sc = _ids(m.find_closest_neighbours("item", a, positive=pos[j], negative=neg[j], k=k))
+        assert idx == list(golden_r2["gcn_posneg_idx"][j])
+        np.testing.assert_allclose(sc, golden_r2["gcn_posneg_score"][j], rtol=0, atol=1e-6)
+    rows, sc = m.find_closest_neighbours_batch("item", anchors, k=k, positive=pos, negative=neg)
+    np.testing.assert_array_equal(rows.cpu().numpy() - len(users), golden_r2["gcn_posneg_idx"])
+    np.testing.assert_allclose(sc.cpu().numpy(), golden_r2["gcn_posneg_score"], rtol=0, atol=1e-6)
+    # positives only / negatives only, default k = 200, batched with ragged lists (None entries)
+    one_anchor, one_pos, one_neg = [], [], []
+    for u in g["user_anchors"][16:20]:
+        p, n = posneg_lists(int(u), len(items))
+        one_anchor += [users[int(u)], users[int(u)]]
+        one_pos += [[items[t] for t in p], None]
+        one_neg += [None, [items[t] for t in n]]
+    rows, sc = m.find_closest_neighbours_batch("item", one_anchor, positive=one_pos, negative=one_neg)
+    np.testing.assert_array_equal(rows.cpu().numpy() - len(users), golden_r2["gcn_one_sided_idx"])
+    np.testing.assert_allclose(sc.cpu().numpy(), golden_r2["gcn_one_sided_score"], rtol=0, atol=1e-6)
+
+
+def test_knn_query_and_embeddings_match_reference(c1_model, golden_r2, hw):
+    m, users, items = c1_model["base"], c1_model["users"], c1_model["items"]
+    u0 = int(golden_r2["knn_query_user"][0])
+    p, n = posneg_lists(u0, len(items))
+    emb = m._query_embedding(users[u0], [items[t] for t in p], [items[t] for t in n])
+    res = m.knn.query(emb, "item", k=25)                                    # MultiKNN.query, :78-83
+    assert [int(x.node_external_id) for x, _ in res] == list(golden_r2["knn_query_idx"])
+    np.testing.assert_allclose([d for _, d in res], golden_r2["knn_query_dist"], rtol=0, atol=1e-6)
+    assert all(a <= b for (_, a), (_, b) in zip(res, res[1:]))
+    probe = [users[3], items[7], hw.Node("user", "ghost"), items[1681], hw.Node("item", "ghost2")]
+    np.testing.assert_array_equal(m.get_embeddings(probe), golden_r2["emb_rows"])       # :146-151, exact copies
+    np.testing.assert_allclose(m.get_average_embeddings([items[1], items[2], items[3]]), golden_r2["avg_a"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(m.get_average_embeddings([users[5], hw.Node("item", "ghost3")]), golden_r2["avg_b"],
+                               rtol=0, atol=1e-6)
+
+
+def _eval_models(hw, golden_eval):
+    nu, ni, dd = [int(x) for x in golden_eval["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, int(golden_eval["seeds"][0]))
+    users = [hw.Node("user", i) for i in range(nu)]
+    items = [hw.Node("item", i) for i in range(ni)]
+    tr, vl = synthetic_edges(nu, ni, int(golden_eval["seeds"][1]))
+    train = [hw.Edge(users[u], items[i], w) for u, i, w in tr]
+    val = [hw.Edge(users[u], items[i], w) for u, i, w in vl]
+    base = hw.ContentRecommendation(None, {"user", "item"}, n_dims=dd)
+    base.fit(users + items, train, None, vectors=O.unit_length(collab, axis=1))
+    return base, users, items, train, val, collab, tr, vl
+
+
+def test_ncf_eval_matches_reference(hw, golden_eval, golden_r2):
+    """validation.ncf_eval (hwer/validation.py:68-97) under the reference's seed: same negatives, device pair
+    scores, device rank / HR@10 / NDCG@10 -- equal to the reference's own numbers, and rank by rank to the oracle."""
+    import random
+    base, users, items, train, val, collab, tr, vl = _eval_models(hw, golden_eval)
+    all_items = [x for x in set([i for u, i, w in val] + [i for u, i, w in train]) if x.node_type == "item"]
+    random.seed(int(golden_r2["ncf_eval_seed"][0]))
+    got = hw.validation.ncf_eval(base, train, val, all_items)
+    np.testing.assert_allclose([got["ncf_hr"], got["ncf_ndcg"]], golden_r2["ncf_eval"], rtol=0, atol=1e-9)
+    # device ranks against the oracle's per-user ranks on identical scores
+    rs = np.random.RandomState(3)
+    s_np = rs.rand(500, 101).astype(np.float32)
+    s_np[::7, 5] = s_np[::7, 0]                       # ties with the positive: the positive stays ahead
+    out, rank = hw.ops.hit_rank_metrics(torch.from_numpy(s_np).cuda(), topn=10, want_rank=True)
+    want_rank = (s_np[:, 1:] > s_np[:, :1]).sum(1)
+    np.testing.assert_array_equal(rank.cpu().numpy(), want_rank)
+    hit = want_rank < 10
+    np.testing.assert_allclose(out.cpu().numpy(), [hit.mean(), np.where(hit, 1 / np.log2(want_rank + 2.0) / (1 + 1e-8), 0).mean()],
+                               rtol=0, atol=1e-12)
+
+
+def test_get_topk_hook_is_honoured(hw, golden_eval):
+    """extraction_efficiency(model, train, val, get_topk, node_type) calls the hook it is given
+    (hwer/validation.py:100,111) and evaluates what it returns."""
+    base, users, items, train, val, collab, tr, vl = _eval_models(hw, golden_eval)
+    calls = []
+
+    def reference_style_hook(model, anchors, node_type):           # hwer/validation.py:30-35
+        calls.append(len(anchors))
+        return {u: model.find_closest_neighbours(node_type, u) for u in anchors}
+
+    ref = dict(zip([str(k) for k in golden_eval["metric_keys"]], golden_eval["metric_values"]))
+    res = hw.validation.extraction_efficiency(base, train, val, reference_style_hook, "item")
+    assert calls and calls[0] == len(set(u for u, i, w in tr) | set(u for u, i, w in vl))
+    for key in ("recall@100", "ndcg_b@100", "ndcg_b@10", "recall@10", "diversity"):
+        assert abs(res["metrics"][key] - ref[key]) < 1e-9
+
+    def empty_hook(model, anchors, node_type):
+        return {}
+    res = hw.validation.extraction_efficiency(base, train, val, empty_hook, "item")
+    assert res["metrics"]["recall@100"] == 0.0 and res["metrics"]["diversity"] == 0.0
+
+
+@pytest.mark.parametrize("B,k,d", [(7, 10, 64), (3, 200, 100), (130, 100, 128), (2, 1000, 32), (1, 1, 8)])
+def test_rerank_conventions(hw, B, k, d):
+    """hwer_rerank against numpy: the four score conventions, the stable order, missing rows, a row map."""
+    n = max(2 * k, 500)
+    t_np, t = unit_table(n, d, 91)
+    rs = np.random.RandomState(92)
+    rows = np.stack([rs.choice(n, k, replace=False) for _ in range(B)]).astype(np.int64)
+    if k > 4:
+        rows[0, k - 2:] = -1                                   # missing results stay last
+        rows[-1, 1] = rows[-1, 0]                              # a duplicate: equal scores keep the input order
+    anchors = rs.randint(0, n, B).astype(np.int64)
+    q_np = (t_np[anchors] + 0.3 * rs.standard_normal((B, d)).astype(np.float32)).astype(np.float32)
+    rows_t, anchors_t, q_t = torch.from_numpy(rows).cuda(), torch.from_numpy(anchors).cuda(), torch.from_numpy(q_np).cuda()
+    safe = np.where(rows >= 0, rows, 0)
+
+    def check(conv, scores, descending, **kw):
+        got_rows, got_sc = hw.ops.rerank(t, rows_t, conv, **kw)
+        got_rows, got_sc = got_rows.cpu().numpy(), got_sc.cpu().numpy()
+        for b in range(B):
+            valid = np.flatnonzero(rows[b] >= 0)
+            key = -scores[b, valid] if descending else scores[b, valid]
+            order = valid[np.argsort(key, kind="stable")]
+            np.testing.assert_array_equal(got_rows[b, :len(order)], rows[b, order])
+            np.testing.assert_allclose(got_sc[b, :len(order)], scores[b, order], rtol=0, atol=1e-6)
+            assert (got_rows[b, len(order):] == -1).all()
+            assert np.isinf(got_sc[b, len(order):]).all()
+
+    pair = ((t_np[anchors][:, None, :] * t_np[safe]).sum(2) + 1) / 2
+    pair_dev = hw.ops.pair_score(t, anchors_t[:, None].expand(B, k).reshape(-1).contiguous(),
+                                 torch.from_numpy(safe).cuda().reshape(-1)).reshape(B, k).cpu().numpy()
+    check("pair", pair_dev.astype(np.float64), True, anchor_rows=anchors_t)     # bit-equal to predict()'s kernel
+    np.testing.assert_allclose(pair_dev, pair, atol=1e-6)
+    dist = np.sqrt(((t_np[safe].astype(np.float64) - q_np[:, None, :].astype(np.float64)) ** 2).sum(2))
+    check("dist", (2 - dist) / 2, True, queries=q_t)
+    check("euclid", dist, False, queries=q_t)
+    given = rs.rand(B, k).astype(np.float32)
+    given[:, k // 2:] = given[:, :k - k // 2]                   # many exact ties
+    check("given", given.astype(np.float64), True, given=torch.from_numpy(given).cuda())
+    # rows local to a gathered index: out rows are the mapped (global) ones
+    perm = rs.permutation(n).astype(np.int64)
+    got_rows, got_sc = hw.ops.rerank(t, rows_t, "dist", queries=q_t, row_map=torch.from_numpy(perm).cuda())
+    dist_m = np.sqrt(((t_np[perm[safe]].astype(np.float64) - q_np[:, None, :].astype(np.float64)) ** 2).sum(2))
+    for b in range(B):
+        valid = np.flatnonzero(rows[b] >= 0)
+        order = valid[np.argsort(-((2 - dist_m[b, valid]) / 2), kind="stable")]
+        np.testing.assert_array_equal(got_rows[b, :len(order)].cpu().numpy(), perm[rows[b, order]])
+    with pytest.raises(RuntimeError):
+        hw.ops.rerank(t.cpu(), rows_t, "pair", anchor_rows=anchors_t)
+
+
+def test_api_path_launches_no_torch_compute(c1_model, hw):
+    """find_closest_neighbours_batch runs search, score convention and ordering in this library's kernels: the only
+    torch kernels allowed on the path are copies / fills (host -> device uploads of row ids)."""
+    from torch.profiler import ProfilerActivity, profile
+    m, users = c1_model["gcn"], c1_model["users"]
+    anchors = users[:64]
+    m.find_closest_neighbours_batch("item", anchors, k=100)
+    for model in (c1_model["gcn"], c1_model["base"]):
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            model.find_closest_neighbours_batch("item", anchors, k=100)
+            torch.cuda.synchronize()
+        names = [e.key for e in prof.key_averages() if getattr(e, "device_type", None) is not None
+                 and str(e.device_type).endswith("CUDA")]
+        bad = [x for x in names if x.startswith("void at::") or "at::native" in x]
+        bad = [x for x in bad if not any(t in x.lower() for t in ("copy", "fill", "memcpy", "memset"))]
+        assert not bad, bad
+        assert any("rerank_kernel" in x for x in names), names
+
+
 # ----------------------------------------------------------------------------- BASELINE.json full size (config C4)
 def test_full_size_properties_10m(hw):
     """10M x 128, top-100 (the headline workload): properties that do not need a CPU pass over the table."""
@@ -676,3 +874,34 @@ def test_full_size_properties_10m(hw):
     bidx, _ = index.topk(q, k, "bf16")
     rec = np.mean([len(set(a) & set(b)) / k for a, b in zip(bidx.cpu().tolist(), idx.cpu().tolist())])
     assert rec >= 0.97
+
+    # ---- the batches bench.py times: B = 4096 (16 query blocks, 8 filter launches, spill_cap 64) and B = 1, each
+    # against an independent fp64 pass over the whole table, and against the B = 64 schedule's answer
+    def full_pass(qv):
+        return torch.cat([table[b:b + 1_000_000].double() @ qv.double() for b in range(0, n, 1_000_000)])
+
+    q4k = torch.cat([q, hw.ops.unit_length(torch.randn((4096 - B, d), generator=gen, device="cuda"))])
+    idx4, _, s4 = index.topk(q4k, k, want_f64=True)
+    assert torch.equal(idx4[:B], idx) and torch.equal(s4[:B], s64)              # same rows as the B = 64 schedule
+    assert bool((s4[:, :-1] >= s4[:, 1:]).all())
+    srt = idx4.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                              # no duplicates in any of the 4096 lists
+    for j in (64, 1999, 4095):
+        full = full_pass(q4k[j])
+        kth = s4[j, -1].item()
+        assert int((full > kth + 1e-12).sum().item()) <= k - 1 and int((full >= kth - 1e-12).sum().item()) >= k
+        assert set(torch.topk(full, k).indices.cpu().tolist()) == set(idx4[j].cpu().tolist())
+        np.testing.assert_allclose(full[idx4[j]].cpu().numpy(), s4[j].cpu().numpy(), atol=1e-12)
+    for j in (0, 777):
+        idx1, _, s1 = index.topk(q4k[j:j + 1].contiguous(), k, want_f64=True)   # B = 1: the HBM-bound schedule
+        assert torch.equal(idx1[0], idx4[j]) and torch.equal(s1[0], s4[j])
+    # 2-shard and 8-shard merges of the B = 4096 batch equal the single-index answer bit for bit
+    for G in (2, 8):
+        parts = []
+        for g in range(G):
+            b, e = hw.sharded.partition(n, G, g)
+            parts.append(hw.sharded.ShardedTopK(table[b:e], b, shadow=shadow[b:e], max_norm=mx).local_topk(q4k, k))
+        midx, _, ms64 = hw.ops.merge_topk(torch.stack([h[1] for h in parts]).contiguous(),
+                                          torch.stack([h[0] for h in parts]).contiguous(), want_f64=True)
+        assert torch.equal(midx, idx4) and torch.equal(ms64, s4)
+        del parts

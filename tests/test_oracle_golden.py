@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import hwer_oracle as O
-from conftest import GOLDEN, synthetic_case, synthetic_edges
+from conftest import GOLDEN, posneg_lists, synthetic_case, synthetic_edges
 
 
 @pytest.fixture(scope="module")
@@ -254,3 +254,64 @@ def test_c3_find_closest_neighbours_matches_reference(golden_c3):
     ua = golden_c3["user_anchors"]
     idx, sc = O.exact_topk(table[nu:], table[ua], k)
     np.testing.assert_array_equal(idx, golden_c3["user_idx"])
+
+
+# ----------------------------------------------------------------------------- round 2 fixtures (reference_r2.npz)
+def test_gcn_posneg_scores_are_distances_to_the_composed_embedding(c1, golden_r2):
+    """GcnNCF.find_closest_neighbours with positive / negative lists (hwer/gcn_ncf.py:363-383)."""
+    g, items, users = c1["g"], c1["items"], c1["users"]
+    r = O.OracleRecommender({"user", "item"}, n_dims=c1["table"].shape[1], gcn_scores=True)
+    r.add_nodes(users + items)
+    r.build_knn(c1["table"])
+    for j, u in enumerate(g["user_anchors"][:16]):
+        p, n = posneg_lists(int(u), len(items))
+        idx, sc = _ids(r.find_closest_neighbours("item", users[int(u)], [items[t] for t in p], [items[t] for t in n],
+                                                 k=c1["k"]))
+        assert idx == list(golden_r2["gcn_posneg_idx"][j])
+        np.testing.assert_allclose(sc, golden_r2["gcn_posneg_score"][j], rtol=0, atol=1e-9)
+    j = 0
+    for u in g["user_anchors"][16:20]:
+        p, n = posneg_lists(int(u), len(items))
+        for pos, neg in (([items[t] for t in p], None), (None, [items[t] for t in n])):
+            idx, sc = _ids(r.find_closest_neighbours("item", users[int(u)], pos, neg))
+            assert idx == list(golden_r2["gcn_one_sided_idx"][j])
+            np.testing.assert_allclose(sc, golden_r2["gcn_one_sided_score"][j], rtol=0, atol=1e-9)
+            j += 1
+
+
+def test_knn_query_and_embeddings_match_reference(c1, golden_r2):
+    r, items, users = c1["rec"], c1["items"], c1["users"]
+    u0 = int(golden_r2["knn_query_user"][0])
+    p, n = posneg_lists(u0, len(items))
+    emb = r.query_embedding(users[u0], [items[t] for t in p], [items[t] for t in n])
+    res = r.knn.query(emb, "item", k=25)
+    assert [int(x.node_external_id) for x, _ in res] == list(golden_r2["knn_query_idx"])
+    np.testing.assert_allclose([d for _, d in res], golden_r2["knn_query_dist"], rtol=0, atol=1e-12)
+    probe = [users[3], items[7], O.Node("user", "ghost"), items[1681], O.Node("item", "ghost2")]
+    np.testing.assert_array_equal(r.get_embeddings(probe), golden_r2["emb_rows"])
+    np.testing.assert_array_equal(r.get_average_embeddings([items[1], items[2], items[3]]), golden_r2["avg_a"])
+    np.testing.assert_array_equal(r.get_average_embeddings([users[5], O.Node("item", "ghost3")]), golden_r2["avg_b"])
+
+
+def eval_case(mod, golden_eval):
+    """The 300 x 500 evaluation case of oracle/make_golden.py with `mod`'s Node type: (table, users, items, train, val)."""
+    nu, ni, dd = [int(x) for x in golden_eval["shape"]]
+    _, collab = synthetic_case(nu, ni, dd, int(golden_eval["seeds"][0]))
+    users = [mod.Node("user", i) for i in range(nu)]
+    items = [mod.Node("item", i) for i in range(ni)]
+    tr, vl = synthetic_edges(nu, ni, int(golden_eval["seeds"][1]))
+    return O.unit_length(collab, axis=1), users, items, tr, vl
+
+
+def test_ncf_eval_matches_reference(golden_eval, golden_r2):
+    import random
+    table, users, items, tr, vl = eval_case(O, golden_eval)
+    m = O.OracleRecommender({"user", "item"}, n_dims=table.shape[1])
+    m.add_nodes(users + items)
+    m.build_knn(table)
+    train = [(users[u], items[i], w) for u, i, w in tr]
+    val = [(users[u], items[i], w) for u, i, w in vl]
+    all_items = [x for x in set([i for u, i, w in val] + [i for u, i, w in train]) if x.node_type == "item"]
+    random.seed(int(golden_r2["ncf_eval_seed"][0]))
+    hr, nd, _ = O.ncf_eval(m, train, val, all_items, random)
+    np.testing.assert_allclose([hr, nd], golden_r2["ncf_eval"], rtol=0, atol=1e-12)
