@@ -4,6 +4,8 @@ exact top-100 by cosine over a synthetic 10M x 128 unit-norm catalogue, item-sha
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
+  python bench.py --workload c3|c5|c2 ...                  # the other BASELINE.json configs (see run_c3 / run_c2;
+                                                           # c5 = the C4 code path at 62.5M rows per GPU, top-1000)
 
 One JSON line on stdout (rank 0).  A "step" is one batch of `--batch` queries answered against the whole
 catalogue.  `value` = queries/s with queries and catalogue resident in HBM; `e2e` = the same through the public
@@ -23,6 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "top-100 cosine queries/sec @10Mx128 items"
+METRIC_C5 = "top-1000 cosine queries/sec @500Mx128 items (62.5M rows per GPU)"
+METRIC_C3 = "top-100 cosine queries/sec, all 138,493 users x 27,278 items x d=256"
 UNIT = "queries/s"
 CHUNK = 1_000_000          # rows generated per seeded chunk: the table is the same for every shard count
 
@@ -33,9 +37,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--items", type=int, default=10_000_000)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "c3", "c2"])
+    ap.add_argument("--items", type=int, default=None)
     ap.add_argument("--dim", type=int, default=128)
-    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--no-extras", action="store_true", help="c4: skip the c3 / c2 summary blocks of the default line")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--mode", default="exact", choices=["exact", "bf16"])
     ap.add_argument("--alpha", type=float, default=0.5)
@@ -45,7 +51,15 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: result exchange over NVLink peer stores fused into the final kernel, or NCCL all-gather")
-    return ap.parse_args()
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload == "c5":        # configs[4]: 500M x 128 over 8 GPUs = 62.5M rows per GPU, top-1000 (weak scaling in N)
+        a.items = a.items or 62_500_000 * world
+        a.k = a.k or 1000
+    else:
+        a.items = a.items or 10_000_000
+        a.k = a.k or 100
+    return a
 
 
 def peaks():
@@ -267,6 +281,21 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if a.workload in ("c3", "c2"):
+        if a.workload == "c3":
+            line = run_c3(a, hw, torch, dist, dev, world, rank)
+        else:
+            c2 = run_c2(a, hw, torch, dev) if rank == 0 else None
+            line = c2 and {"metric": "validation.extraction_efficiency seconds, ML-1M shape", "value": c2["seconds"],
+                           "unit": "s", "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": c2["seconds"] * 1e3,
+                           "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64 metrics",
+                           "data": "synthetic", "config": {"workload": c2["workload"]}, "c2": c2}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     pk = peaks()
     begin, end = hw.sharded.partition(a.items, world, rank)
     table, shadow, blend_ms, blend_bytes = make_shard(hw, torch, a, begin, end, dev)
@@ -303,6 +332,8 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    stages = {}                      # per-step ms of the last profiled pass: filter / select / final / exchange
+
     def measure(B, steps, warmup, profile):
         q = queries_for(B)
         for _ in range(warmup):
@@ -322,6 +353,9 @@ def run_b200(a):
         rc, need = index.finish()
         if rc != 0:
             raise RuntimeError("candidate overflow in the timed region (needed cap %d)" % need)
+        stages.clear()
+        if profile:
+            stages.update({k_: v_ / steps for k_, v_ in index.profile_stages().items()})
         filt_ms, filt_l, other_l = index.profile_read() if profile else (0.0, 0, 0)
         index.profile(False)
         return ms, filt_ms, filt_l, other_l, out
@@ -337,10 +371,12 @@ def run_b200(a):
         if B >= 256:
             flops = 2.0 * B * rows * a.dim
             ach = flops / (filt_ms_per_step * 1e-3) / 1e12
-            return dict({"bound": "tensor", "achieved": ach, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / pk["tc_sustained"], "basis": pk["basis"] + " (sustained bf16: the kernel is "
-                         "timed inside a long power-capped step)", "peak_burst": pk["tc_burst"],
-                         "frac_of_burst": ach / pk["tc_burst"], "algorithmic_flops": flops}, **extra)
+            # the timed region of the default run is a fraction of a second: the burst cuBLAS figure is the basis
+            # (the sustained, power-capped one is reported next to it)
+            return dict({"bound": "tensor", "achieved": ach, "peak": pk["tc_burst"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tc_burst"], "basis": pk["basis"] + " (burst bf16 cuBLAS)",
+                         "peak_sustained": pk["tc_sustained"], "frac_of_sustained": ach / pk["tc_sustained"],
+                         "algorithmic_flops": flops}, **extra)
         ach = byt / (filt_ms_per_step * 1e-3) / 1e9
         return dict({"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                      "basis": pk["basis"] + " (copy bandwidth)"}, **extra)
@@ -384,30 +420,53 @@ def run_b200(a):
     launches_per_step = (filt_l + other_l) / a.steps + (1 if world > 1 and a.exchange == "nccl" else 0)
     roof = roofline(a.batch, filt_ms / a.steps)
     roof["share_of_step"] = (filt_ms / a.steps) / (pms / a.steps)
-    if roof["bound"] == "tensor":
-        # which measured peak applies: the sustained (power-capped) cuBLAS figure when this run's SM clock was held
-        # well below its maximum during the timed region, the burst figure otherwise (short per-GPU steps at N > 1)
-        capped = bool(clocks) and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and \
-            clocks["sm_mhz"] < 0.93 * clocks["sm_max_mhz"]
-        if not capped or roof["frac"] > 1.0:
-            roof["peak"], roof["frac"] = roof["peak_burst"], roof["frac_of_burst"]
-            roof["basis"] = pk["basis"] + " (burst bf16: the SM clock was not held down by the power cap, or the " \
-                                          "kernel outran the sustained cuBLAS figure)"
-
-    # ---- end to end through the public API: pinned host queries in, results out, every step
-    q_host = queries_for(a.batch).cpu().pin_memory()
+    stage_ms = dict(stages, step=pms / a.steps)
+    # ---- end to end.  N = 1: through the reference-facing API, model.find_closest_neighbours_batch(node_type, anchors,
+    # k) -- Node -> row lookup on the host, anchor rows copied in, query composition, search, score convention +
+    # per-anchor ordering, rows and scores copied out to pinned host memory, every step.  The 10M items are a node
+    # RANGE of the model (no Python object per item); the anchors are real Node objects.
+    # N > 1: ShardedTopK.topk with pinned-host query vectors in and [B, k] results out on every rank (the hwer model
+    # classes serve one GPU; the sharded index is the multi-GPU entry point).
     idx_host = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
-    sc_host = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+    e2e_api = None
+    if world == 1 and a.workload == "c4":
+        users = [hw.Node("user", i) for i in range(a.batch)]
+        table_all = torch.cat([queries_for(a.batch), table])
+        shadow_all = torch.cat([hw.ops.make_shadow(table_all[:a.batch]), shadow])
+        shard = index = table = shadow = None          # the model below owns the (one) copy of the tables
+        torch.cuda.empty_cache()
+        model = hw.ContentRecommendation(None, {"user", "item"}, n_dims=a.dim, mode=a.mode)
+        model.add_nodes(users)
+        model.add_node_range("item", a.items)
+        model.__build_knn__(table_all, shadow=shadow_all)
+        model.fit_done = True
+        index = model.knn.knn["item"]
+        table, shadow = table_all[a.batch:], shadow_all[a.batch:]
+        shard = None
+        sc_host = torch.empty((a.batch, a.k), dtype=torch.float64).pin_memory()
+        e2e_api = "ContentRecommendation.find_closest_neighbours_batch('item', <%d user Nodes>, k=%d)" % (a.batch, a.k)
+        h2d, d2h = a.batch * 8, a.batch * a.k * 16
 
-    def step_e2e():
-        q = q_host.to(dev, non_blocking=True)
-        if world > 1:
-            idx, sc = shard.topk(q, a.k, a.mode)
-        else:
-            idx, sc = index.topk(q, a.k, a.mode, idx_offset=begin)
-        idx_host.copy_(idx, non_blocking=True)
-        sc_host.copy_(sc, non_blocking=True)
-        torch.cuda.synchronize()
+        def step_e2e():
+            rows, sc = model.find_closest_neighbours_batch("item", users, k=a.k)
+            idx_host.copy_(rows, non_blocking=True)
+            sc_host.copy_(sc, non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        q_host = queries_for(a.batch).cpu().pin_memory()
+        sc_host = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+        e2e_api = "ShardedTopK.topk(<pinned host queries>, k=%d)" % a.k if world > 1 else "TopKIndex.topk"
+        h2d, d2h = a.batch * a.dim * 4, a.batch * a.k * 12
+
+        def step_e2e():
+            q = q_host.to(dev, non_blocking=True)
+            if world > 1:
+                idx, sc = shard.topk(q, a.k, a.mode)
+            else:
+                idx, sc = index.topk(q, a.k, a.mode, idx_offset=begin)
+            idx_host.copy_(idx, non_blocking=True)
+            sc_host.copy_(sc, non_blocking=True)
+            torch.cuda.synchronize()
 
     for _ in range(max(1, a.warmup)):
         step_e2e()
@@ -418,15 +477,21 @@ def run_b200(a):
         step_e2e()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    api_same = None
+    if world == 1 and a.workload == "c4":
+        # the API answers in global rows (users first): the same items as the device-resident pass (an anchor's row is
+        # re-normalised by the API, so a k-th / (k+1)-th pair closer than ~1e-8 may swap: reported, not asserted)
+        api_same = int(idx_host.sum().item()) - a.batch * a.k * a.batch == int(out[0].sum().item())
 
     sweep = {}
-    if world == 1 and a.sweep:
+    if a.sweep:
         for B in [int(x) for x in a.sweep.split(",") if x]:
             st = max(a.steps, 20)
             sms, sf, _, _, _ = measure(B, st, a.warmup, profile=False)
             _, sf, _, _, _ = measure(B, st, 1, profile=True)
             r = roofline(B, sf / st)
-            sweep[str(B)] = {"value": B * st / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / st, "roofline": r}
+            sweep[str(B)] = {"value": B * st / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / st, "roofline": r,
+                             "stage_ms": dict(stages)}
 
     if rank == 0:
         cpu = None
@@ -435,13 +500,14 @@ def run_b200(a):
             cpu = cpu_baseline(table[:rows].cpu().numpy(), queries_for(64).cpu().numpy(), a.k, a.items, a.cpu_seconds)
         idx_chk = out[0]
         line = {
-            "metric": METRIC, "value": a.batch * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC if a.workload == "c4" else METRIC_C5, "value": a.batch * a.steps / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 tensor-core filter + f64 re-score" if a.mode == "exact" else "bf16",
+            "scaling": "strong" if a.workload == "c4" else "weak", "vs_baseline": None, "dtype": "bf16 tensor-core filter + f64 re-score" if a.mode == "exact" else "bf16",
             "data": "synthetic",
-            "config": {"workload": "C4: synthetic 10M x 128 unit-norm catalogue (alpha=%.2f blend of two seeded Gaussian "
+            "config": {"workload": "%s: synthetic %s x %d unit-norm catalogue (alpha=%.2f blend of two seeded Gaussian "
                                    "tables), exact top-%d by cosine, query batch %d, item-sharded over %d GPU(s)"
-                                   % (a.alpha, a.k, a.batch, world),
+                                   % (a.workload.upper(), "{:,}".format(a.items), a.dim, a.alpha, a.k, a.batch, world),
                        "items": a.items, "dim": a.dim, "k": a.k, "batch": a.batch, "mode": a.mode,
                        "parallelism": ("item-shard x%d + %s" % (world, "peer-store exchange fused into the final kernel + owner merge"
                                                                       if a.exchange == "p2p" else "NCCL all-gather + merge"))
@@ -449,8 +515,9 @@ def run_b200(a):
                        "l2": "inputs larger than L2 (%.2f GB bf16 shadow per GPU streamed every step)"
                              % ((end - begin) * d_pad * 2 / 1e9)},
             "e2e": {"value": a.batch * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12,
-                    "ms_per_step": e2e_ms / e2e_steps},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": e2e_api, "same_items_as_device_pass": api_same},
+            "stage_ms": stage_ms,
             "gpu_launches": int(round(launches_per_step * a.steps)),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sweep": sweep,
             "blend_normalize": {"achieved": blend_bytes / (blend_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
@@ -459,13 +526,181 @@ def run_b200(a):
         }
         if exchange_note:
             line["config"]["exchange_note"] = exchange_note
+        if world == 1 and a.workload == "c4" and not a.no_extras:
+            # summary blocks of the other single-GPU configs (full lines: --workload c3 / c2)
+            try:
+                c3 = run_c3(a, hw, torch, dist, dev, 1, 0, steps=max(3, a.steps // 4), cpu=False)
+                line["c3"] = {k_: c3[k_] for k_ in ("metric", "value", "unit", "ms_per_step", "e2e", "stage_ms", "roofline")}
+            except Exception as ex:                                   # the headline line must not die with an extra
+                line["c3"] = {"error": str(ex)[:200]}
+            try:
+                line["c2"] = run_c2(a, hw, torch, dev)
+            except Exception as ex:
+                line["c2"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        if shard._px is not None:
-            shard._px.check()
         shard.close()
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- C3: all users, small catalogue
+def run_c3(a, hw, torch, dist, dev, world, rank, steps=None, cpu=True):
+    """BASELINE.json configs[2]: ML-20M shape, 138,493 users x 27,278 items, d = 256, top-100 for EVERY user.  The
+    27.9 MB item table is replicated; the users (queries) are sharded over the ranks, no collective on the data path.
+    A step = one pass over all users.  `value`: anchor rows resident on the device; `e2e`: the hwer API with Node
+    anchors, rows + scores copied to pinned host memory."""
+    U, I, d, k = 138_493, 27_278, 256, 100
+    steps = steps or a.steps
+    g1 = torch.Generator(device=dev).manual_seed(600)
+    g2 = torch.Generator(device=dev).manual_seed(601)
+    table, shadow = hw.ops.blend_normalize(torch.randn((U + I, d), generator=g1, device=dev),
+                                           torch.randn((U + I, d), generator=g2, device=dev), a.alpha)
+    users = [hw.Node("user", i) for i in range(U)]
+    items = [hw.Node("item", i) for i in range(I)]
+    model = hw.ContentRecommendation(None, {"user", "item"}, n_dims=d, mode=a.mode)
+    model.add_nodes(users + items)
+    model.__build_knn__(table, shadow=shadow)
+    model.fit_done = True
+    b, e = hw.sharded.partition(U, world, rank)
+    my_users = users[b:e]
+    my_rows = torch.arange(b, e, dtype=torch.int64, device=dev)
+    index = model.knn.knn["item"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(a.warmup, 3)):
+        out = model.find_closest_neighbours_batch("item", my_rows, k=k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = model.find_closest_neighbours_batch("item", my_rows, k=k)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    index.profile(True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.find_closest_neighbours_batch("item", my_rows, k=k)
+    torch.cuda.synchronize()
+    pms = (time.perf_counter() - t0) * 1e3
+    stages = {k_: v_ / steps for k_, v_ in index.profile_stages().items()}
+    filt_ms, filt_l, other_l = index.profile_read()
+    index.profile(False)
+    idx_host = torch.empty((e - b, k), dtype=torch.int64).pin_memory()
+    sc_host = torch.empty((e - b, k), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        rows, sc = model.find_closest_neighbours_batch("item", my_users, k=k)
+        idx_host.copy_(rows, non_blocking=True)
+        sc_host.copy_(sc, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    pk = peaks()
+    flops = 2.0 * (e - b) * I * d
+    ach = flops / (filt_ms / steps * 1e-3) / 1e12 if filt_ms > 0 else 0.0
+    line = {
+        "metric": METRIC_C3, "value": U * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16 tensor-core filter + f64 re-score", "data": "synthetic",
+        "config": {"workload": "C3: ML-20M shape, %d users x %d items, d=%d, exact top-%d for every user through "
+                               "find_closest_neighbours_batch; item table replicated, users sharded over %d GPU(s), "
+                               "no data-path collective" % (U, I, d, k, world),
+                   "users": U, "items": I, "dim": d, "k": k, "parallelism": "query-shard x%d" % world,
+                   "l2": "the 14 MB bf16 item table is L2-resident by design; every step streams %d MB of anchors and "
+                         "writes %d MB of results" % ((e - b) * d * 4 // 2**20, (e - b) * k * 16 // 2**20)},
+        "e2e": {"value": U * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (e - b) * 8,
+                "d2h_bytes_per_step": (e - b) * k * 16, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "ContentRecommendation.find_closest_neighbours_batch('item', <%d user Nodes>, k=%d)" % (e - b, k)},
+        "gpu_launches": int(filt_l + other_l) + 2 * steps,
+        "stage_ms": dict(stages, step=pms / steps),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tc_burst"], "unit": "TFLOP/s", "frac": ach / pk["tc_burst"],
+                     "basis": pk["basis"] + " (burst bf16 cuBLAS)", "algorithmic_flops": flops,
+                     "kernel": "score_filter_tc_kernel over this rank's users", "ms_per_step": filt_ms / steps,
+                     "share_of_step": (filt_ms / steps) / (pms / steps), "traffic": None,
+                     "note": "the contraction is %.2f TFLOP per pass: the step is bound by per-query selection, "
+                             "re-scoring and result traffic, not by the tensor pipe" % (flops / 1e12)},
+        "result_checksum": int(out[0].sum().item()),
+    }
+    if cpu and rank == 0 and not a.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import hwer_oracle as O
+        t_np = table.cpu().numpy()
+        m = O.OracleRecommender({"user", "item"}, n_dims=d)
+        ou = [O.Node("user", i) for i in range(U)]
+        m.add_nodes(ou + [O.Node("item", i) for i in range(I)])
+        tb = time.time()
+        m.build_knn(t_np)
+        build_s = time.time() - tb
+        n, t0 = 0, time.time()
+        while time.time() - t0 < a.cpu_seconds:
+            O.model_get_topk_knn(m, ou[n:n + 8], "item", k=k)
+            n += 8
+        dt = time.time() - t0
+        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "oracle port of validation.model_get_topk_knn (serial find_closest_neighbours, "
+                                          "sklearn KDTree float64) over the full %d x %d item table for the first %d of "
+                                          "%d users in %.1f s; tree build %.1f s excluded" % (I, d, n, U, dt, build_s)}
+    return line
+
+
+# --------------------------------------------------------------------------------------------- C2: full validation pass
+def run_c2(a, hw, torch, dev):
+    """BASELINE.json configs[1]: ML-1M shape (6,040 users x 3,706 items, d = 128): one validation.extraction_efficiency
+    call end to end -- top-200 for every edge source, train-item filter, Recall@K / NDCG / diversity on the device,
+    ncf_eval -- on the inputs of tests/golden/reference_c2.npz, whose metric values (from the reference itself) the
+    result is checked against.  `reference_seconds` is what the unmodified reference took in the build container."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import random
+    from conftest import synthetic_case, synthetic_edges
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_c2.npz"))
+    nu, ni, d = [int(x) for x in g["shape"]]
+    _, collab = synthetic_case(nu, ni, d, int(g["seeds"][0]))
+    users = [hw.Node("user", i) for i in range(nu)]
+    items = [hw.Node("item", i) for i in range(ni)]
+    tr, vl = synthetic_edges(nu, ni, int(g["seeds"][1]))
+    train = [hw.Edge(users[u], items[i], w) for u, i, w in tr]
+    val = [hw.Edge(users[u], items[i], w) for u, i, w in vl]
+    model = hw.GcnNCF(None, {"user", "item"}, n_dims=d)
+    model.fit(users + items, train, None, collaborative_vectors=collab)
+    hw.validation.extraction_efficiency(model, train[:2000], val[:200], None, "item")       # warm-up (allocations)
+    random.seed(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = hw.validation.extraction_efficiency(model, train, val, None, "item")
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    want = dict(zip([str(x) for x in g["metric_keys"]], g["metric_values"]))
+    err = max(abs(res["metrics"][k_] - v_) for k_, v_ in want.items())
+    ref_s = 58.7
+    return {"workload": "C2: ML-1M shape, %d users x %d items, d=%d: validation.extraction_efficiency end to end "
+                        "(%d train / %d validation edges)" % (nu, ni, d, len(train), len(val)),
+            "seconds": secs, "retrieval_seconds": res["metrics"]["retrieval_time"],
+            "reference_seconds": ref_s, "reference_retrieval_seconds": float(g["retrieval_time"][0]),
+            "reference_seconds_source": "the unmodified reference run by oracle/make_golden_c2c3.py in the build container "
+                                        "(8 vCPU, single-threaded path)",
+            "speedup_vs_reference": ref_s / secs, "max_metric_error_vs_reference": err,
+            "metrics": {k_: res["metrics"][k_] for k_ in want}}
 
 
 if __name__ == "__main__":

@@ -40,6 +40,7 @@ SIGNATURES = {
     "hwer_topk_finish": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
     "hwer_profile": (c_int, [c_void_p, c_int]),
     "hwer_profile_read": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
+    "hwer_profile_stages": (c_int, [c_void_p, c_void_p, POINTER(c_double)]),
     "hwer_profile_launches": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int32, POINTER(c_int32)]),
     "hwer_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "hwer_merge_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -73,6 +73,7 @@ struct hwer_index {
     float* thr = nullptr;
     float* margin = nullptr;
     float* floor = nullptr;
+    float* qmax = nullptr;
     size_t ws_queries = 0, ws_cap = 0;
     uint4* spill = nullptr;                // hit entries of the filter rounds (FilterParams::spill)
     unsigned int* spill_cnt = nullptr;
@@ -84,9 +85,14 @@ struct hwer_index {
     // tuning knobs (HWER_FIRST_ROWS / HWER_GROWTH / HWER_LATE_ROWS), read once when the index is created
     long long env_first_rows = 0, env_late_rows = 0;
     int env_growth = 0;
+    // HWER_DISABLE bit mask for A/B runs (measured in profiles/r02_*_ab.txt): 1 = bias MMA instead of scaled queries,
+    // 2 = only the full-capacity final shape; and three alternatives that measured no better and are off by default:
+    // 4 = warp-per-query final, 8 = spill extraction fused into the filter kernel, 16 = warp-per-query dense select
+    int env_disable = 0;
     // optional live profiling of the dominant (filter) kernel with CUDA events on the launching stream
     bool prof = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    std::vector<int> ev_stage;             // what each bracket timed: 0 filter (+ extract), 1 select, 2 final, 3 exchange
     size_t ev_used = 0;
     long long filter_launches = 0, other_launches = 0;
 };
@@ -107,12 +113,14 @@ int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
     if (ix->margin) cudaFree(ix->margin);
     if (ix->floor) cudaFree(ix->floor);
     if (ix->ovf) cudaFree(ix->ovf);
-    ix->floor = nullptr; ix->ovf = nullptr;
+    if (ix->qmax) cudaFree(ix->qmax);
+    ix->floor = nullptr; ix->ovf = nullptr; ix->qmax = nullptr;
     ix->cand = nullptr; ix->cnt = nullptr; ix->thr = nullptr; ix->margin = nullptr;
     ix->ws_queries = ix->ws_cap = 0;
     if (cudaMalloc(&ix->cand, q * c * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ix->cnt, q * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&ix->ovf, q * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&ix->qmax, q * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&ix->thr, q * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&ix->margin, q * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&ix->floor, q * sizeof(float)) != cudaSuccess) {
@@ -129,8 +137,13 @@ int ensure_workspace(hwer_index* ix, size_t queries, size_t cap) {
 int ensure_spill(hwer_index* ix, int Bc, int k, int growth) {
     if (!ix->use_tc) return HWER_OK;
     const double per_thread = 1.4 * k * growth * (double)Bc / (double)hwer::filter_tc_spill_buffers(ix->num_sms);
+    // ceiling: 128 entries per thread (465 MB), or 512 (1.9 GB) when HBM has room -- top-1000 at batch 4096
+    // (config C5) expects ~150 entries per thread and round, and a full buffer means blocking appends
+    size_t free_b = 0, total_b = 0;
+    int ceiling = 128;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > ((size_t)16 << 30)) ceiling = 512;
     int want = 16;
-    while (want < 2.0 * per_thread + 8.0 && want < 128) want <<= 1;
+    while (want < 2.0 * per_thread + 8.0 && want < ceiling) want <<= 1;
     if (want <= ix->spill_cap) return HWER_OK;      // grow-only: a larger buffer serves every smaller request
     HWER_CUDA(cudaDeviceSynchronize());
     if (ix->spill) cudaFree(ix->spill);
@@ -145,13 +158,17 @@ int ensure_spill(hwer_index* ix, int Bc, int k, int growth) {
     return HWER_OK;
 }
 
-bool prof_begin(hwer_index* ix, cudaStream_t stream) {
+enum : int { kStageFilter = 0, kStageSelect = 1, kStageFinal = 2, kStageExchange = 3, kStages = 4 };
+
+bool prof_begin(hwer_index* ix, cudaStream_t stream, int stage = kStageFilter) {
     if (!ix->prof) return false;
     if (ix->ev_used == ix->ev.size()) {
         cudaEvent_t a, b;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
         ix->ev.emplace_back(a, b);
+        ix->ev_stage.push_back(stage);
     }
+    ix->ev_stage[ix->ev_used] = stage;
     cudaEventRecord(ix->ev[ix->ev_used].first, stream);
     return true;
 }
@@ -280,16 +297,18 @@ int hwer_index_create(hwer_index_t** out, const float* table_f32_dev, const void
         if (mul < 1 || ix->n_tiles < 8) mul = 1;
         ix->tile_mul = mul;
     }
-    if (cudaMalloc(&ix->needed_dev, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMallocHost(&ix->needed_host, sizeof(unsigned int)) != cudaSuccess) {
+    // [0] largest candidate-list demand seen by any kernel of the pending calls, [1] a wait on a peer GPU timed out
+    if (cudaMalloc(&ix->needed_dev, 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMallocHost(&ix->needed_host, 2 * sizeof(unsigned int)) != cudaSuccess) {
         delete ix;
         return fail(HWER_E_NOMEM, "hwer_index_create: allocation failed");
     }
-    cudaMemset(ix->needed_dev, 0, sizeof(unsigned int));
-    *ix->needed_host = 0;
+    cudaMemset(ix->needed_dev, 0, 2 * sizeof(unsigned int));
+    ix->needed_host[0] = ix->needed_host[1] = 0;
     if (const char* e = getenv("HWER_FIRST_ROWS")) ix->env_first_rows = atoll(e);
     if (const char* e = getenv("HWER_GROWTH")) ix->env_growth = atoi(e);
     if (const char* e = getenv("HWER_LATE_ROWS")) ix->env_late_rows = atoll(e);
+    if (const char* e = getenv("HWER_DISABLE")) ix->env_disable = atoi(e);
     *out = ix;
     return HWER_OK;
 }
@@ -304,6 +323,7 @@ int hwer_index_destroy(hwer_index_t* ix) {
     if (ix->margin) cudaFree(ix->margin);
     if (ix->floor) cudaFree(ix->floor);
     if (ix->ovf) cudaFree(ix->ovf);
+    if (ix->qmax) cudaFree(ix->qmax);
     if (ix->spill) cudaFree(ix->spill);
     if (ix->spill_cnt) cudaFree(ix->spill_cnt);
     if (ix->needed_dev) cudaFree(ix->needed_dev);
@@ -368,7 +388,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         HWER_CUDA(hwer::launch_fill_f32(ix->thr, Bc, -INFINITY, stream));
         // the CUDA-core path scores in fp32: its (tiny) margin keeps even bf16-less indexes exact
         const float* margin = (exact || !ix->use_tc) ? ix->margin : nullptr;
-        HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->max_norm, ix->margin, ix->floor, stream));
+        HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->max_norm, ix->margin, ix->floor, ix->qmax, stream));
         ix->other_launches += 3;   // fill + margin/floor + final
         long long seen = 0;
         int round = 0;
@@ -389,13 +409,16 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
                 if (nq > nq_max) nq = nq_max;
                 p.nq = nq; p.nqb = (Bc + nq - 1) / nq;
-                p.thr = ix->thr; p.floor = ix->floor; p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
+                // bf16 mode returns the tensor-core scores themselves: they must be products of the RN-bf16 query
+                // (not of a per-round rescaled one), so it keeps the bias MMA
+                p.thr = ix->thr; p.floor = ix->floor; p.qmax = ix->qmax; p.force_bias = (ix->env_disable & 1) | (exact ? 0 : 1); p.cand = ix->cand; p.cnt = ix->cnt; p.cap = sch.cap;
                 p.n_items = ix->n; p.tile_begin = (int)seen_l; p.tile_end = (int)end;
                 p.tile_mul = ix->tile_mul; p.tile_mod = T;
                 p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics
                 p.spill = ix->spill; p.spill_cnt = ix->spill_cnt; p.spill_cap = ix->spill_cap; p.spill_ctas = ix->num_sms;
+                p.fused_extract = (ix->env_disable & 8) ? 1 : 0;
                 HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
-                if (round > 0) ix->other_launches += 1;     // spill_extract_kernel rides behind every filter round
+                if (round > 0 && !p.fused_extract) ix->other_launches += 1;     // spill_extract_kernel behind the filter
             } else {
                 long long rb = seen_l * hwer::kTileItems, re = end * hwer::kTileItems;
                 if (re > ix->n) re = ix->n;
@@ -404,27 +427,23 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
             }
             prof_end(ix, stream, timed);
             const int fixed = (ix->use_tc && round == 0) ? (int)((end - seen_l) * hwer::kTileItems) : -1;
+            const bool timed_sel = prof_begin(ix, stream, kStageSelect);
+            hwer::SelExchange sx;
+            memset(&sx, 0, sizeof sx);
             if (share_thr) {
-                // each shard publishes its ceil(k/G)-th best score so far to every peer; the min over shards bounds
-                // the global k-th best from below (DESIGN.md "Multi-GPU"), so all shards filter with ~1/G the hits
-                hwer::SelExchange sx;
-                memset(&sx, 0, sizeof sx);
-                sx.world = xv->world; sx.rank = xv->rank; sx.b_cap = xv->b_cap; sx.parity = round & 1; sx.q0 = q0;
+                // each shard publishes its ceil(k/G)-th best score so far to every peer; the min over shards bounds the
+                // global k-th best from below (DESIGN.md "Multi-GPU"), so all shards filter with ~1/G the hits.
+                // Publish, wait and compaction happen inside the one select launch, query by query.
+                sx.mode = hwer::kSelShared;
+                sx.world = xv->world; sx.rank = xv->rank; sx.b_cap = xv->b_cap; sx.k_share = k_share; sx.q0 = q0;
                 sx.epoch = (call_epoch * 64u + (unsigned int)chunk_idx) * 64u + (unsigned int)round + 1u;
                 sx.flags = xv->flags[xv->rank];
                 for (int r = 0; r < xv->world; ++r) sx.thr_x[r] = xv->thr_x[r];
-                sx.mode = hwer::kSelKthToPeers;
-                HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k_share, fixed, margin, ix->thr,
-                                                      ix->needed_dev, ix->ovf, &sx, stream));
-                HWER_CUDA(hwer::launch_exchange_signal(*xv, 4, sx.epoch, stream));
-                sx.mode = hwer::kSelCompactMin;
-                HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
-                                                      ix->needed_dev, ix->ovf, &sx, stream));
-                ix->other_launches += 2;
-            } else {
-                HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
-                                                      ix->needed_dev, ix->ovf, nullptr, stream));
             }
+            HWER_CUDA(hwer::launch_select_compact(ix->cand, ix->cnt, sch.cap, Bc, k, fixed, margin, ix->thr,
+                                                  ix->needed_dev, ix->ovf, share_thr ? &sx : nullptr,
+                                                  (ix->env_disable & 16) ? 1 : 0, stream));
+            prof_end(ix, stream, timed_sel);
             ix->filter_launches += 1;
             ix->other_launches += 1;
             seen = end_s;
@@ -432,11 +451,15 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
         }
         hwer::PeerDst pd;
         if (peer) { pd = *peer; pd.q0 = q0; }
+        // small batches keep the 512-thread shape: with a handful of queries the latency of ONE list is the stage's time
+        const bool timed_fin = prof_begin(ix, stream, kStageFinal);
         HWER_CUDA(hwer::launch_final(ix->cand, ix->cnt, sch.cap, Bc, k, exact ? 1 : 0, ix->table, ix->d, Q, idx_offset,
                                      peer ? nullptr : (long long*)out_idx_dev + (size_t)q0 * k,
                                      peer ? nullptr : out_score_dev + (size_t)q0 * k,
                                      (!peer && out_score64_dev) ? out_score64_dev + (size_t)q0 * k : nullptr,
-                                     ix->needed_dev, ix->ovf, peer ? &pd : nullptr, stream));
+                                     ix->needed_dev, ix->ovf, peer ? &pd : nullptr,
+                                     (ix->env_disable & 2) || Bc < 256 ? 0 : ((ix->env_disable & 4) ? 1 : 2), stream));
+        prof_end(ix, stream, timed_fin);
     }
     return HWER_OK;
 }
@@ -470,7 +493,7 @@ ExchangeLayout exchange_layout(int world, int b_cap, int k_cap) {
     L.out_idx = off; off += align256(o * 8);
     L.out_score64 = off; off += align256(o * 8);
     L.out_score = off; off += align256(o * 4);
-    L.thr_x = off; off += align256((size_t)2 * world * b_cap * sizeof(float));
+    L.thr_x = off; off += align256((size_t)world * b_cap * sizeof(unsigned long long));
     L.total = off;
     return L;
 }
@@ -546,9 +569,11 @@ int hwer_exchange_create(hwer_exchange_t** out, int32_t world, int32_t rank, int
         x->v.out_idx[r] = reinterpret_cast<long long*>(b + L.out_idx);
         x->v.out_score64[r] = reinterpret_cast<double*>(b + L.out_score64);
         x->v.out_score[r] = reinterpret_cast<float*>(b + L.out_score);
-        x->v.thr_x[r] = reinterpret_cast<float*>(b + L.thr_x);
+        x->v.thr_x[r] = reinterpret_cast<unsigned long long*>(b + L.thr_x);
     }
     x->device = device;
+    cudaError_t pe = hwer::exchange_preload();
+    if (pe != cudaSuccess) { delete x; return fail_cuda(pe, "hwer_exchange_create: loading the exchange kernels"); }
     *out = x;
     return HWER_OK;
 }
@@ -580,7 +605,7 @@ int hwer_topk_sharded(hwer_index_t* ix, hwer_exchange_t* x, const float* queries
         if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));
         if (phases & HWER_PHASE_COLLECT)
             HWER_CUDA(hwer::launch_exchange_collect(x->v, B, k, epoch, (long long*)out_idx_dev, out_score_dev,
-                                                    out_score64_dev, stream));
+                                                    out_score64_dev, ix->needed_dev, stream));
         return HWER_OK;
     }
     hwer::PeerDst pd;
@@ -591,11 +616,13 @@ int hwer_topk_sharded(hwer_index_t* ix, hwer_exchange_t* x, const float* queries
                        // tiny batches are launch-bound, not hit-bound: the two extra launches per round do not pay
                        (x->share_thresholds && B > 16) ? &x->v : nullptr, epoch, stream_v);
     if (rc) return rc;
-    HWER_CUDA(hwer::launch_exchange_signal(x->v, 0, epoch, stream));
+    const bool timed_x = prof_begin(ix, stream, kStageExchange);
+    HWER_CUDA(hwer::launch_exchange_signal(x->v, 0, epoch, ix->needed_dev, stream));
     if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));
     if (phases & HWER_PHASE_COLLECT)
         HWER_CUDA(hwer::launch_exchange_collect(x->v, B, k, epoch, (long long*)out_idx_dev, out_score_dev,
-                                                out_score64_dev, stream));
+                                                out_score64_dev, ix->needed_dev, stream));
+    prof_end(ix, stream, timed_x);
     ix->other_launches += 3;
     return HWER_OK;
 }
@@ -639,11 +666,12 @@ int hwer_topk_finish(hwer_index_t* ix, void* stream_v, uint32_t* needed_cap) {
     if (!ix) return fail(HWER_E_INVALID, "hwer_topk_finish: null index");
     cudaStream_t stream = (cudaStream_t)stream_v;
     HWER_CUDA(cudaSetDevice(ix->device));
-    HWER_CUDA(cudaMemcpyAsync(ix->needed_host, ix->needed_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    HWER_CUDA(cudaMemsetAsync(ix->needed_dev, 0, sizeof(unsigned int), stream));
+    HWER_CUDA(cudaMemcpyAsync(ix->needed_host, ix->needed_dev, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    HWER_CUDA(cudaMemsetAsync(ix->needed_dev, 0, 2 * sizeof(unsigned int), stream));
     HWER_CUDA(cudaStreamSynchronize(stream));
-    const unsigned int need = *ix->needed_host;
+    const unsigned int need = ix->needed_host[0];
     if (needed_cap) *needed_cap = need;
+    if (ix->needed_host[1]) return fail(HWER_E_PEER, "hwer_topk_sharded: timed out waiting for a peer GPU");
     if (need > ix->last_cap) {
         char buf[160];
         snprintf(buf, sizeof buf, "hwer_topk: candidate lists overflowed (cap %u, needed %u): re-run with a larger cap",
@@ -668,6 +696,7 @@ int hwer_profile_read(hwer_index_t* ix, void* stream_v, double* filter_ms, int64
     HWER_CUDA(cudaStreamSynchronize((cudaStream_t)stream_v));
     double ms = 0.0;
     for (size_t i = 0; i < ix->ev_used; ++i) {
+        if (ix->ev_stage[i] != kStageFilter) continue;
         float t = 0.f;
         HWER_CUDA(cudaEventElapsedTime(&t, ix->ev[i].first, ix->ev[i].second));
         ms += t;
@@ -684,11 +713,29 @@ int hwer_profile_launches(hwer_index_t* ix, void* stream_v, double* out_ms, int3
     if (!ix || !n_out || cap < 0 || (cap > 0 && !out_ms)) return fail(HWER_E_INVALID, "hwer_profile_launches: bad argument");
     HWER_CUDA(cudaSetDevice(ix->device));
     HWER_CUDA(cudaStreamSynchronize((cudaStream_t)stream_v));
-    *n_out = (int32_t)ix->ev_used;
-    for (size_t i = 0; i < ix->ev_used && i < (size_t)cap; ++i) {
+    int32_t n = 0;
+    for (size_t i = 0; i < ix->ev_used; ++i) {
+        if (ix->ev_stage[i] != kStageFilter) continue;
+        if (n < cap) {
+            float t = 0.f;
+            HWER_CUDA(cudaEventElapsedTime(&t, ix->ev[i].first, ix->ev[i].second));
+            out_ms[n] = t;
+        }
+        ++n;
+    }
+    *n_out = n;
+    return HWER_OK;
+}
+
+int hwer_profile_stages(hwer_index_t* ix, void* stream_v, double* out4_ms) {
+    if (!ix || !out4_ms) return fail(HWER_E_INVALID, "hwer_profile_stages: bad argument");
+    HWER_CUDA(cudaSetDevice(ix->device));
+    HWER_CUDA(cudaStreamSynchronize((cudaStream_t)stream_v));
+    for (int s = 0; s < kStages; ++s) out4_ms[s] = 0.0;
+    for (size_t i = 0; i < ix->ev_used; ++i) {
         float t = 0.f;
         HWER_CUDA(cudaEventElapsedTime(&t, ix->ev[i].first, ix->ev[i].second));
-        out_ms[i] = t;
+        out4_ms[ix->ev_stage[i]] += t;
     }
     return HWER_OK;
 }

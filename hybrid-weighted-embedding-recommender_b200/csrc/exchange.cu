@@ -40,7 +40,7 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 }
 
 // flags layout per rank (unsigned int[64]): [0..7] phase-0 epoch per source rank, [8..15] phase-1 epoch per owner,
-// [16] merge CTA counter, [17] error (a wait timed out)
+// [16] merge CTA counter, [17] error (a wait timed out), [40..47] candidate-capacity demand of each source rank
 __device__ bool wait_epoch(const unsigned int* flag, unsigned int epoch, unsigned int* err) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
@@ -53,7 +53,11 @@ __device__ bool wait_epoch(const unsigned int* flag, unsigned int epoch, unsigne
     return true;
 }
 
-__global__ void exchange_signal_kernel(const __grid_constant__ ExchangeView v, int phase, unsigned int epoch) {
+__global__ void exchange_signal_kernel(const __grid_constant__ ExchangeView v, int phase, unsigned int epoch,
+                                       const unsigned int* __restrict__ needed) {
+    // this rank's candidate-capacity demand rides with the flag: every rank learns the largest one from its own
+    // memory (exchange_collect_kernel), so an overflow retry is agreed without a host-side collective
+    if (needed && (int)threadIdx.x < v.world) v.flags[threadIdx.x][40 + v.rank] = *needed;
     // everything this stream wrote before (the final kernels' peer stores) is ordered before the flags
     __threadfence_system();
     if ((int)threadIdx.x < v.world) st_release_sys(v.flags[threadIdx.x] + phase * kMaxPeers + v.rank, epoch);
@@ -136,10 +140,15 @@ exchange_merge_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsi
 __global__ void __launch_bounds__(256)
 exchange_collect_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsigned int epoch,
                         long long* __restrict__ out_idx, float* __restrict__ out_score,
-                        double* __restrict__ out_score64) {
+                        double* __restrict__ out_score64, unsigned int* __restrict__ status2) {
     unsigned int* myflags = v.flags[v.rank];
     if ((int)threadIdx.x < v.world) wait_epoch(myflags + kMaxPeers + threadIdx.x, epoch, myflags + 17);
     __syncthreads();
+    if (status2 && blockIdx.x == 0 && (int)threadIdx.x < v.world) {
+        // every source's phase-0 flag (and with it its capacity demand) arrived long before its owners finished
+        if (wait_epoch(myflags + threadIdx.x, epoch, myflags + 17)) atomicMax(status2, __ldcv(myflags + 40 + threadIdx.x));
+        if (__ldcv(myflags + 17)) atomicMax(status2 + 1, 1u);
+    }
     const size_t n = (size_t)B * K;
     const long long* si = v.out_idx[v.rank];
     const float* ss = v.out_score[v.rank];
@@ -153,15 +162,28 @@ exchange_collect_kernel(const __grid_constant__ ExchangeView v, int B, int K, un
 
 }  // namespace
 
-cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned int epoch, cudaStream_t stream) {
-    exchange_signal_kernel<<<1, 32, 0, stream>>>(v, phase, epoch);
+// CUDA loads a kernel's code on its first launch (lazy module loading), and that load can wait for the device to go
+// idle.  A host thread that first launches an exchange kernel while a select kernel of the same process is already
+// spinning on a peer (one process driving several ranks, or a peer that is late) would stall behind that spin, so
+// every kernel of this file is loaded when the exchange object is created.
+cudaError_t exchange_preload() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, exchange_signal_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, exchange_merge_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, exchange_collect_kernel);
+    return e;
+}
+
+cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned int epoch, const unsigned int* needed,
+                                   cudaStream_t stream) {
+    exchange_signal_kernel<<<1, 32, 0, stream>>>(v, phase, epoch, needed);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, cudaStream_t stream) {
     long long own = (long long)B - (long long)v.rank * v.q_per_owner;
     if (own > v.q_per_owner) own = v.q_per_owner;
-    if (own <= 0) return launch_exchange_signal(v, 1, epoch, stream);      // nothing to merge: just report in
+    if (own <= 0) return launch_exchange_signal(v, 1, epoch, nullptr, stream);      // nothing to merge: just report in
     int P = 2;
     while (P < v.world * K) P <<= 1;
     const size_t smem = (size_t)P * 16;
@@ -175,12 +197,12 @@ cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned 
 }
 
 cudaError_t launch_exchange_collect(const ExchangeView& v, int B, int K, unsigned int epoch, long long* out_idx,
-                                    float* out_score, double* out_score64, cudaStream_t stream) {
+                                    float* out_score, double* out_score64, unsigned int* status2, cudaStream_t stream) {
     const size_t n = (size_t)B * K;
     int grid = (int)((n + 256 * 8 - 1) / (256 * 8));
     if (grid < 1) grid = 1;
     if (grid > 296) grid = 296;
-    exchange_collect_kernel<<<grid, 256, 0, stream>>>(v, B, K, epoch, out_idx, out_score, out_score64);
+    exchange_collect_kernel<<<grid, 256, 0, stream>>>(v, B, K, epoch, out_idx, out_score, out_score64, status2);
     return cudaGetLastError();
 }
 

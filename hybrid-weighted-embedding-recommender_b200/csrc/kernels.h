@@ -16,8 +16,9 @@ constexpr int kMaxPeers = 8;         // GPUs of one node
 // Proven bound on |bf16-tensor-core score - exact score| / (|q| * |x|):
 // two round-to-nearest bf16 roundings (2^-9 each) plus fp32 accumulation of
 // d_pad products.  See DESIGN.md "Exactness".
+// (+ 2^-22: a query block may be staged as q * (1 / thr), two more fp32 roundings of the query operand.)
 inline float bf16_score_eps_rel(int d_pad) {
-    return 0.00390625f + 3.8147e-6f + float(d_pad) * 2.3841858e-7f;
+    return 0.00390625f + 3.8147e-6f + 2.3841858e-7f + float(d_pad) * 2.3841858e-7f;
 }
 inline float f32_score_eps_rel(int d) { return float(d) * 2.3841858e-7f; }
 
@@ -32,6 +33,10 @@ struct FilterParams {
     int qb_step;              // query blocks advanced per outer iteration (= gridDim.x / slots)
     const float* thr;         // [B] current per-query admission threshold
     const float* floor;       // [B] finite lower bound of any score of the query (stands in for thr = -inf)
+    const float* qmax;        // [B] largest |component| of the query (overflow guard of the scaled filter)
+    int fused_extract;        // 1: the filter CTA turns its own spill entries into candidates at the end of each query
+                              // block; 0 (A/B knob): spill_extract_kernel is launched behind the filter kernel
+    int force_bias;           // A/B knob: filter every query block with the bias MMA (never scale the queries)
     unsigned long long* cand; // [B, cap] packed candidate keys
     unsigned int* cnt;        // [B] candidate counters (may exceed cap => overflow)
     unsigned int cap;
@@ -65,29 +70,29 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
                                long long row_begin, long long row_end, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float max_norm, float* margin,
-                                float* floor, cudaStream_t stream);
+                                float* floor, float* qmax, cudaStream_t stream);
 cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream);
 
 // Cross-GPU threshold sharing for a row-sharded catalogue (DESIGN.md "Multi-GPU"): with G shards, the min over
 // shards of each shard's ceil(K/G)-th best score so far is a lower bound of the GLOBAL K-th best, and a much
 // tighter one than a shard's own K-th best -- so every shard admits ~1/G as many candidates per round.
-//   kSelKthToPeers : select the kth best of the local list and store it (no margin) into every peer's thr_x slot
-//   kSelCompactMin : wait for every shard's value of this round, thr = min - margin, compact the local list
-enum : int { kSelLocal = 0, kSelKthToPeers = 1, kSelCompactMin = 2 };
+//   kSelShared : select the k_share-th best of the local list, store {epoch, score} into every peer's slot of the
+//                query, wait for the G words of the query, thr = min - margin, compact the local list (one kernel)
+enum : int { kSelLocal = 0, kSelShared = 1 };
 struct SelExchange {
     int mode;                        // kSelLocal: no exchange (single GPU)
     int world, rank;
     int b_cap;                       // row length of thr_x
-    int parity;                      // rounds alternate between two halves of thr_x
+    int k_share;                     // ceil(K / world)
     long long q0;                    // global query index of this launch's first query
-    unsigned int epoch;              // flags[32 + g] >= epoch <=> shard g has published this round's values
-    float* thr_x[kMaxPeers];         // per rank: [2][world][b_cap]
-    unsigned int* flags;             // this rank's flag block
+    unsigned int epoch;              // this round's epoch; a slot is ready when its epoch is >= this
+    unsigned long long* thr_x[kMaxPeers];   // per rank: [world][b_cap] words {epoch << 32 | fp32 score bits}
+    unsigned int* flags;             // this rank's flag block ([17] = error)
 };
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
-                                  unsigned int* ovf, const SelExchange* sx, cudaStream_t stream);
+                                  unsigned int* ovf, const SelExchange* sx, int dense_warp, cudaStream_t stream);
 
 // Where final_kernel stores a query's result when the catalogue is sharded over several GPUs: straight into the
 // exchange buffer of the GPU that owns (merges) that query, over NVLink peer stores (exchange.cu).
@@ -105,7 +110,7 @@ struct PeerDst {
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,
                          long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
-                         unsigned int* ovf, const PeerDst* peer, cudaStream_t stream);
+                         unsigned int* ovf, const PeerDst* peer, int allow_small, cudaStream_t stream);
 
 // Exhaustive exact search of ONE query at a time (the answer of last resort for a query whose candidate list cannot
 // hold everything inside the bf16 margin, e.g. tens of thousands of duplicate rows): fp64 scores of every row with
@@ -119,8 +124,8 @@ cudaError_t launch_bruteforce_topk(const float* table, long long n, int d, const
 // of the merged rows to every rank; final wait + copy-out.
 struct ExchangeView {
     int world, rank, q_per_owner, q_cap, k_cap, b_cap;
-    unsigned int* flags[kMaxPeers];      // per rank: [2][kMaxPeers] epochs, [16] counter, [17] error, [32..39] threshold epochs
-    float* thr_x[kMaxPeers];             // per rank: [2][world][b_cap] shared-threshold slots
+    unsigned int* flags[kMaxPeers];      // per rank: [2][kMaxPeers] epochs, [16] counter, [17] error, [40..47] needed cap per source
+    unsigned long long* thr_x[kMaxPeers];   // per rank: [world][b_cap] shared-threshold words {epoch, score}
     long long sched_rows;                // rows of the largest shard: every rank walks the same round schedule
     double* xs[kMaxPeers];
     long long* xi[kMaxPeers];
@@ -128,10 +133,14 @@ struct ExchangeView {
     float* out_score[kMaxPeers];
     double* out_score64[kMaxPeers];
 };
-cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned int epoch, cudaStream_t stream);
+cudaError_t exchange_preload();      // loads the exchange kernels now (see exchange.cu)
+// `needed` (phase 0, may be NULL): this rank's candidate-capacity demand, delivered to every peer with the flag
+cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned int epoch, const unsigned int* needed,
+                                   cudaStream_t stream);
 cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, cudaStream_t stream);
+// status2 (may be NULL): [0] is raised (atomicMax) to the largest capacity demand of any rank, [1] set on a peer timeout
 cudaError_t launch_exchange_collect(const ExchangeView& v, int B, int K, unsigned int epoch, long long* out_idx,
-                                    float* out_score, double* out_score64, cudaStream_t stream);
+                                    float* out_score, double* out_score64, unsigned int* status2, cudaStream_t stream);
 
 cudaError_t launch_merge(const double* scores, const long long* idx, int G, int B, int K, long long* out_idx,
                          float* out_score, double* out_score64, cudaStream_t stream);

@@ -14,7 +14,7 @@
 //   UMMA N = nq <= 256 queries   (B operand: resident in shared memory for the CTA's lifetime)
 //   UMMA K = 16, d_pad/16 steps  (accumulators: fp32 in TMEM, acc_stages-deep)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
-// warps 2..17 = epilogue (tcgen05.ld -> release the accumulator -> sign test of score - thr -> 48-byte spill entry
+// warps 2..17 = epilogue (tcgen05.ld -> release the accumulator -> max-of-8 test of score / thr -> 48-byte spill entry
 // for a group of 8 columns with a hit; spill_extract_kernel behind the filter kernel appends the candidates).
 #include "common.cuh"
 #include "kernels.h"
@@ -74,30 +74,49 @@ __device__ __forceinline__ float query_threshold(const FilterParams& p, int q) {
 
 // Buffer full: blocking append of the hits of one 8-column group.  Out of line, rarely taken.
 __device__ __noinline__ void append_group_direct(const FilterParams* p, uint4 a, uint4 b, uint32_t thr_addr,
-                                                 uint32_t row, int q0) {
+                                                 uint32_t row, int q0, bool scaled) {
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
-        const float diff = __uint_as_float(w[j]);
-        if (diff >= 0.0f) {
+        const float val = __uint_as_float(w[j]);          // score / thr (scaled block) or score - thr (biased block)
+        if (scaled ? val >= 1.0f : val >= 0.0f) {
             float thr;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(thr_addr + (uint32_t)j * 4u));
             const unsigned int slot = atomicAdd(&p->cnt[q0 + j], 1u);
-            if (slot < p->cap) p->cand[(size_t)(q0 + j) * p->cap + slot] = make_key(diff + thr, row);
+            if (slot < p->cap) p->cand[(size_t)(q0 + j) * p->cap + slot] = make_key(scaled ? val * thr : val + thr, row);
         }
     }
 }
 
-// The filter rounds fold the threshold into the MMA: one extra K=16 step multiplies a constant-ones slab with
-// (-thr_hi, -thr_lo), so the accumulator already holds score - thr and "is any of these 8 scores admissible"
-// is "is any sign bit clear": the bitwise AND of the eight words keeps the sign bit only if all are negative.
+// The filter rounds make "is any of these 8 scores admissible" a handful of 3-input ALU instructions, two ways.
+//
+// SCALED query blocks (every threshold of the block positive -- the normal case once round 0 has run): the query
+// is staged as q / thr, so the accumulator holds score / thr and a score is admissible iff its word is >= 1.0f:
+// the maximum of the eight words (FMNMX3; NaN operands are ignored, so NaN scores never admit) against 1.0f.
+// No extra tensor-pipe work: a tile is exactly d_pad / 16 MMAs.
+//
+// BIASED query blocks (some threshold <= 0: tiny or anti-correlated catalogues, k close to n): one extra K=16 MMA
+// multiplies a constant-ones slab with (-thr_hi, -thr_lo), the accumulator holds score - thr, and the test is "is
+// any sign bit clear": the bitwise AND of the eight words keeps the sign bit only if all are negative.
 __device__ __forceinline__ uint32_t and8(const uint32_t* v) {
     return (v[0] & v[1] & v[2]) & (v[3] & v[4] & v[5]) & (v[6] & v[7]);
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float max8(const uint32_t* v) {
+    const float m0 = max3f(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    const float m1 = max3f(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    return fmaxf(max3f(__uint_as_float(v[6]), __uint_as_float(v[7]), m0), m1);
+}
+
+// Can this query be filtered in the scaled domain?  thr > 0, and q / thr must stay far from overflow in bf16/fp32
+// (an infinite operand would turn 0 * inf products into NaN scores, which never admit: a true neighbour lost).
+__device__ __forceinline__ bool query_scalable(const FilterParams& p, int q, float thr) {
+    return q >= p.B || (thr > 0.0f && p.qmax[q] < thr * 1.0e30f && !p.force_bias);
 }
 
 // 32 accumulator columns of one catalogue row (already out of TMEM, the accumulator stage already released)
 // against the 32 queries they belong to.
-template <int MODE>
+template <int MODE, bool scaled>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* thr_s, int c0, int q_base,
                                                uint32_t row, bool row_ok, const FilterParams& p, SpillCtx& sp,
                                                uint32_t dense_pos) {
@@ -123,13 +142,21 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
         return;
     }
     uint32_t grp[4];
+    float mx[4];
+    bool any;
+    if (scaled) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) grp[g] = and8(&v[8 * g]);
-    const uint32_t all = (grp[0] & grp[1]) & (grp[2] & grp[3]);
-    if ((int)all >= 0 && row_ok) {                 // this lane's row has a non-negative (score - thr): rare
+        for (int g = 0; g < 4; ++g) mx[g] = max8(&v[8 * g]);
+        any = fmaxf(max3f(mx[0], mx[1], mx[2]), mx[3]) >= 1.0f;
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) grp[g] = and8(&v[8 * g]);
+        any = (int)((grp[0] & grp[1]) & (grp[2] & grp[3])) >= 0;
+    }
+    if (any && row_ok) {                           // this lane's row has an admissible score: rare
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            if ((int)grp[g] >= 0) {
+            if (scaled ? mx[g] >= 1.0f : (int)grp[g] >= 0) {
                 const uint4 a = make_uint4(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3]);
                 const uint4 b = make_uint4(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]);
                 if (sp.n < (uint32_t)p.spill_cap) {
@@ -138,7 +165,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
                     e[1] = b;
                     e[2] = make_uint4(row, (uint32_t)(q_base + c0 + 8 * g), 0u, 0u);
                 } else {
-                    append_group_direct(&p, a, b, smem_u32(thr_s + c0 + 8 * g), row, q_base + c0 + 8 * g);
+                    append_group_direct(&p, a, b, smem_u32(thr_s + c0 + 8 * g), row, q_base + c0 + 8 * g, scaled);
                 }
                 ++sp.n;
             }
@@ -163,7 +190,7 @@ constexpr int kExtractThreads = kEpiWarps * 32 * kExtractSub;
 __global__ void __launch_bounds__(kExtractThreads)
 spill_extract_kernel(const __grid_constant__ FilterParams p) {
     __shared__ unsigned int cnt_s[kMaxNQ];      // hits per query of the block, then the write cursor
-    __shared__ float thr_x[kMaxNQ];             // what the threshold MMA subtracted for the query
+    __shared__ float thr_x[kMaxNQ];             // the query's threshold (scaled block) / what the bias MMA subtracted
     const int tid = threadIdx.x;
     const size_t buf = (size_t)blockIdx.x * (kEpiWarps * 32) + (tid / kExtractSub);
     unsigned int n = p.spill_cnt[buf];
@@ -174,8 +201,13 @@ spill_extract_kernel(const __grid_constant__ FilterParams p) {
     unsigned int cursor = (unsigned int)(tid % kExtractSub);         // this thread's entries: cursor, cursor + Sub, ...
     for (int qb = (int)blockIdx.x / p.slots; qb < p.nqb; qb += p.qb_step) {     // the filter CTA's query blocks
         const int q_base = qb * nq;
-        for (int i = tid; i < nq; i += kExtractThreads) cnt_s[i] = 0u;
-        __syncthreads();
+        bool ok = true;                                                         // the filter CTA's own vote, recomputed
+        for (int i = tid; i < nq; i += kExtractThreads) {
+            cnt_s[i] = 0u;
+            ok = ok && query_scalable(p, q_base + i, query_threshold(p, q_base + i));
+        }
+        const bool scaled = __syncthreads_and(ok ? 1 : 0) != 0;                 // words are score / thr, else score - thr
+        const float admit = scaled ? 1.0f : 0.0f;
         unsigned int end = cursor;
         {                                                                       // pass 1: count
             uint4 a, b, m;
@@ -188,7 +220,7 @@ spill_extract_kernel(const __grid_constant__ FilterParams p) {
                 if (end < n) { const uint4* e = e0 + (size_t)end * 3; a = e[0]; b = e[1]; m = e[2]; }   // next in flight
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (__uint_as_float(w[j]) >= 0.0f) atomicAdd(&cnt_s[ql + j], 1u);
+                    if (__uint_as_float(w[j]) >= admit) atomicAdd(&cnt_s[ql + j], 1u);
             }
         }
         __syncthreads();
@@ -196,7 +228,8 @@ spill_extract_kernel(const __grid_constant__ FilterParams p) {
             const unsigned int c = cnt_s[i];
             if (c) {
                 uint32_t nhi, nlo;
-                thr_x[i] = thr_split(query_threshold(p, q_base + i), nhi, nlo);
+                const float t = query_threshold(p, q_base + i);
+                thr_x[i] = scaled ? t : thr_split(t, nhi, nlo);
                 cnt_s[i] = atomicAdd(&p.cnt[q_base + i], c);
             }
         }
@@ -213,12 +246,14 @@ spill_extract_kernel(const __grid_constant__ FilterParams p) {
                 if (i < end) { const uint4* e = e0 + (size_t)i * 3; a = e[0]; b = e[1]; m = e[2]; }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float diff = __uint_as_float(w[j]);                   // score - thr (NaN stays NaN)
-                    if (diff >= 0.0f) {
+                    const float val = __uint_as_float(w[j]);                    // score / thr or score - thr (NaN stays NaN)
+                    if (val >= admit) {
                         const unsigned int pos = atomicAdd(&cnt_s[ql + j], 1u);
-                        // the key carries score = diff + thr: one fp32 rounding (~3e-8), far inside the margin
+                        // the key carries the score back in query units: one fp32 rounding (~6e-8 relative), far
+                        // inside the margin
                         if (pos < p.cap)
-                            p.cand[(size_t)(q_base + ql + j) * p.cap + pos] = make_key(diff + thr_x[ql + j], row);
+                            p.cand[(size_t)(q_base + ql + j) * p.cap + pos] =
+                                make_key(scaled ? val * thr_x[ql + j] : val + thr_x[ql + j], row);
                     }
                 }
             }
@@ -226,6 +261,62 @@ spill_extract_kernel(const __grid_constant__ FilterParams p) {
         cursor = end;
         __syncthreads();
     }
+}
+
+// The same per-hit work done by the filter CTA itself, at the end of each query block (FilterParams::fused_extract):
+// every epilogue thread walks ITS OWN buffer (its entry count is still in a register, the entries are L2-hot), the
+// CTA counts hits per query in shared memory, reserves one range per query with a single global atomic, and writes
+// the keys.  No second kernel launch per round (launch gap + 37 us of mostly fixed cost at B = 4096), and the
+// thresholds / scaled flag of the block are the ones already in shared memory.  All kThreadsTc threads call this.
+__device__ __forceinline__ void extract_own_spill(const FilterParams& p, const uint4* mine, uint32_t n_raw, int q_base,
+                                                  int nq, const float* thr_s, bool scaled, unsigned int* cnt_s) {
+    const int tid = threadIdx.x;
+    const unsigned int n = n_raw < (uint32_t)p.spill_cap ? n_raw : (uint32_t)p.spill_cap;   // the excess went direct
+    if (__syncthreads_or(n != 0u) == 0) return;                      // nothing spilled by this CTA for this block
+    for (int i = tid; i < nq; i += kThreadsTc) cnt_s[i] = 0u;
+    __syncthreads();
+    const float admit = scaled ? 1.0f : 0.0f;
+    {                                                                 // pass 1: count
+        uint4 a, b, m;
+        if (n) { a = mine[0]; b = mine[1]; m = mine[2]; }
+        for (unsigned int e = 0; e < n;) {
+            const int ql = (int)m.y - q_base;
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            ++e;
+            if (e < n) { const uint4* x = mine + (size_t)e * 3; a = x[0]; b = x[1]; m = x[2]; }      // next in flight
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (__uint_as_float(w[j]) >= admit) atomicAdd(&cnt_s[ql + j], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nq; i += kThreadsTc) {                      // one global atomic per query with hits
+        const unsigned int c = cnt_s[i];
+        if (c) cnt_s[i] = atomicAdd(&p.cnt[q_base + i], c);
+    }
+    __syncthreads();
+    {                                                                 // pass 2: write the keys
+        uint4 a, b, m;
+        if (n) { a = mine[0]; b = mine[1]; m = mine[2]; }
+        for (unsigned int e = 0; e < n;) {
+            const int ql = (int)m.y - q_base;
+            const uint32_t row = m.x;
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            ++e;
+            if (e < n) { const uint4* x = mine + (size_t)e * 3; a = x[0]; b = x[1]; m = x[2]; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float val = __uint_as_float(w[j]);              // score / thr or score - thr (NaN stays NaN)
+                if (val >= admit) {
+                    const unsigned int pos = atomicAdd(&cnt_s[ql + j], 1u);
+                    if (pos < p.cap)
+                        p.cand[(size_t)(q_base + ql + j) * p.cap + pos] =
+                            make_key(scaled ? val * thr_s[ql + j] : val + thr_s[ql + j], row);
+                }
+            }
+        }
+    }
+    __syncthreads();                                                  // cnt_s / thr_s are rewritten by the next block
 }
 
 template <int MODE, int KB>
@@ -245,7 +336,8 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     uint8_t* ones_smem = item_smem + (size_t)p.stages * stage_bytes;   // [128 rows x K16] constant (1, 1, 0, ...)
     uint8_t* bias_smem = ones_smem + kBiasRowBytes * kTileItems;       // [nq rows x K16] (-thr_hi, -thr_lo, 0, ...)
     float* thr_s = reinterpret_cast<float*>(bias_smem + kBiasRowBytes * kMaxNQ);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + kMaxNQ);
+    unsigned int* cnt_s = reinterpret_cast<unsigned int*>(thr_s + kMaxNQ);      // fused extract: hits per query
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + kMaxNQ);
     uint64_t* full_bar = bars;                            // [stages]   TMA -> MMA
     uint64_t* empty_bar = bars + p.stages;                // [stages]   MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * p.stages;            // [acc]      MMA -> epilogue
@@ -309,18 +401,42 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
 
     for (int qb = qb0; qb < p.nqb; qb += p.qb_step) {
         const int q_base = qb * nq;
-        // ---- stage the query block: fp32 -> bf16 (RN), K-major, 128B swizzle ----
+        // ---- thresholds of the block, and how it will be filtered (scaled queries or the bias MMA) ----
+        bool scaled = false;
+        if (MODE == kModeFilter) {
+            bool ok = true;
+            for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
+                const float t = query_threshold(p, q_base + i);
+                thr_s[i] = t;
+                ok = ok && query_scalable(p, q_base + i, t);
+            }
+            scaled = __syncthreads_and(ok ? 1 : 0) != 0;           // also publishes thr_s to the staging loop below
+            if (!scaled) {
+                for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
+                    uint32_t nhi, nlo;
+                    thr_s[i] = thr_split(thr_s[i], nhi, nlo);      // what the bias MMA subtracts
+                    uint8_t* dst = bias_smem + (i >> 3) * 256 + (i & 7) * 16;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(nhi | (nlo << 16), 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < nq; i += kThreadsTc) thr_s[i] = 0.0f;
+        }
+        // ---- stage the query block: fp32 (x 1 / thr in a scaled block) -> bf16 (RN), K-major, 128B swizzle ----
         {
             constexpr int chunks_per_row = KB * 8;   // 16-byte chunks (8 bf16) per query row
             for (int i = threadIdx.x; i < nq * chunks_per_row; i += kThreadsTc) {
                 const int r = i / chunks_per_row;
                 const int c = i - r * chunks_per_row;
                 const int q = q_base + r;
+                // two fp32 roundings (reciprocal, product): 2^-23 relative, inside the margin's slack (kernels.h)
+                const float scale = (scaled && q < p.B) ? 1.0f / thr_s[r] : 1.0f;
                 float f[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = c * 8 + j;
-                    f[j] = (q < p.B && col < p.d) ? __ldg(p.queries + (size_t)q * p.d + col) : 0.0f;
+                    f[j] = (q < p.B && col < p.d) ? __ldg(p.queries + (size_t)q * p.d + col) * scale : 0.0f;
                 }
                 uint4 pk;
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
@@ -334,18 +450,6 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 const int kblk = c >> 3;
                 const int cc = (c & 7) ^ (r & 7);
                 *reinterpret_cast<uint4*>(q_smem + (size_t)kblk * q_slab + r * 128 + cc * 16) = pk;
-            }
-            for (int i = threadIdx.x; i < nq; i += kThreadsTc) {
-                const int q = q_base + i;
-                if (MODE == kModeFilter) {
-                    uint32_t nhi, nlo;
-                    thr_s[i] = thr_split(query_threshold(p, q), nhi, nlo);       // what the MMA subtracts
-                    uint8_t* dst = bias_smem + (i >> 3) * 256 + (i & 7) * 16;
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(nhi | (nlo << 16), 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
-                } else {
-                    thr_s[i] = 0.0f;
-                }
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
         }
@@ -400,7 +504,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                             umma_bf16_lohi(d_tmem, a_lo + k * (kSlabBytes >> 4) + 2 * s, sw_hi,
                                            q_lo + k * q_step + 2 * s, sw_hi, idesc, (k | s) ? 1u : 0u);
                     }
-                    if (MODE == kModeFilter)        // accumulator -= thr (see epilogue_chunk)
+                    if (MODE == kModeFilter && !scaled)     // biased block: accumulator -= thr (see and8 / max8)
                         umma_bf16_lohi(d_tmem, ones_lo, ns_hi, bias_lo, ns_hi, idesc, 1u);
                     umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
                     umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
@@ -441,16 +545,25 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 if (phys >= tile_mod) phys -= tile_mod;
                 const bool row_ok = row < n_items;
                 const uint32_t dense_pos = (uint32_t)(t_first - p.tile_begin + it * p.slots) * (uint32_t)kTileItems + lane_row;
-                epilogue_chunk<MODE>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
-                if (two) epilogue_chunk<MODE>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
+                if (scaled) {
+                    epilogue_chunk<MODE, true>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
+                    if (two) epilogue_chunk<MODE, true>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
+                } else {
+                    epilogue_chunk<MODE, false>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
+                    if (two) epilogue_chunk<MODE, false>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
+                }
             }
         }
         tiles_done += (uint32_t)my_tiles;
         // All MMAs reading this query block have retired once every epilogue warp is here.
         __syncthreads();
+        if (MODE == kModeFilter && p.fused_extract) {
+            extract_own_spill(p, sp.mine, warp >= 2 ? sp.n : 0u, q_base, nq, thr_s, scaled, cnt_s);
+            sp.n = 0u;                                                // the buffer starts over for the next block
+        }
     }
 
-    if (MODE == kModeFilter && warp >= 2)
+    if (MODE == kModeFilter && warp >= 2 && !p.fused_extract)
         p.spill_cnt[(size_t)blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64)] = sp.n;
     tc_fence_before_sync();
     __syncthreads();
@@ -502,16 +615,20 @@ score_filter_simt_kernel(const float* __restrict__ table, long long n_items, int
 }
 
 __global__ void query_margin_kernel(const float* __restrict__ queries, int B, int d, float factor, float max_norm,
-                                    float* __restrict__ margin, float* __restrict__ floor) {
+                                    float* __restrict__ margin, float* __restrict__ floor, float* __restrict__ qmax) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= B) return;
-    float s = 0.0f;
+    float s = 0.0f, mx = 0.0f;
     for (int c = lane_id(); c < d; c += 32) {
         const float v = queries[(size_t)q * d + c];
         s = fmaf(v, v, s);
+        mx = fmaxf(mx, fabsf(v));
     }
     s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane_id() == 0) {
+        qmax[q] = mx;
         const float nrm = sqrtf(s) * 1.0001f;       // rounded up: the bounds must never be under-estimated
         if (margin) margin[q] = factor * nrm;
         // no score of this query can be below -|q| * max|x| (minus the bf16 slack): a finite "-inf"
@@ -565,7 +682,7 @@ cudaError_t launch_tc_variant(int mode, int kb, int grid, size_t smem, const CUt
 }  // namespace
 
 size_t filter_tc_smem_bytes(int nq, int kb, int stages) {
-    return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + kMaxNQ * sizeof(float) +
+    return 1024 + (size_t)kb * nq * 128 + (size_t)stages * kb * kSlabBytes + 2 * kMaxNQ * sizeof(float) +
            (size_t)kBiasRowBytes * (kTileItems + kMaxNQ) +
            (2 * stages + 8) * sizeof(uint64_t) + 16 + kEpiWarps * sizeof(unsigned int);
 }
@@ -604,7 +721,7 @@ cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sm
     if (mode == kModeFilter && (!p.spill || !p.spill_cnt || p.spill_cap < 1 || grid > p.spill_ctas))
         return cudaErrorInvalidValue;
     cudaError_t e = launch_tc_variant(mode, p.kb, grid, smem, tmap, p, stream);
-    if (e != cudaSuccess || mode != kModeFilter) return e;
+    if (e != cudaSuccess || mode != kModeFilter || p.fused_extract) return e;
     spill_extract_kernel<<<grid, kExtractThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -630,9 +747,9 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
 }
 
 cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float max_norm, float* margin,
-                                float* floor, cudaStream_t stream) {
+                                float* floor, float* qmax, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, max_norm, margin, floor);
+    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, max_norm, margin, floor, qmax);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kSelThreads = 256;
 constexpr int kFinalThreads = 512;   // 16 warps re-score candidates concurrently (row gathers are latency bound)
+constexpr int kFinalSmallThreads = 128;
 
 __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
@@ -56,29 +57,43 @@ __device__ __forceinline__ void hist_add_aggregated(unsigned int* hist, bool tak
     if (take) atomicAdd(&hist[bin], 1u);
 }
 
-__device__ __forceinline__ unsigned int sel_ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// ---- cross-GPU threshold sharing inside the select kernels (row-sharded catalogue, DESIGN.md "Multi-GPU") ----
+// Every shard publishes, per query, the ceil(k / G)-th best score of its local list; the min over shards bounds the
+// GLOBAL k-th best from below, so all shards filter the next round with ~1/G the hits.  One 64-bit word per
+// (shard, query) carries {round epoch, score}: a single peer store publishes it and the reader needs no separate
+// flag or fence -- the warp that selected query q publishes q, then spins on its OWN memory until the G words of q
+// carry this round's epoch (or a later one: a shard may already be a round ahead, and its newer bound is just as
+// valid and tighter).  No extra kernel launches, no grid-wide handshake: queries proceed independently.
+__device__ __forceinline__ unsigned long long sel_ld_acquire_sys64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Spin until shard `g` has published this round's thresholds (bounded: a dead peer must not hang the GPU).
-__device__ bool sel_wait_shard(const SelExchange& sx, int g) {
-    const long long t0 = clock64();
-    while ((int)(sel_ld_acquire_sys(sx.flags + 32 + g) - sx.epoch) < 0) {
-        if (clock64() - t0 > 6000000000ll) { atomicExch(sx.flags + 17, 1u); return false; }
-        __nanosleep(100);
-    }
-    return true;
-}
-__device__ __forceinline__ float sel_global_kth(const SelExchange& sx, long long q) {
-    float t = __int_as_float(0x7f800000);
-    for (int g = 0; g < sx.world; ++g)
-        t = fminf(t, __ldcv(sx.thr_x[sx.rank] + ((size_t)sx.parity * sx.world + g) * sx.b_cap + q));
-    return t;
+__device__ __forceinline__ void sel_st_relaxed_sys64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void sel_publish_kth(const SelExchange& sx, long long q, float sk) {
-    for (int g = 0; g < sx.world; ++g)
-        sx.thr_x[g][((size_t)sx.parity * sx.world + sx.rank) * sx.b_cap + q] = sk;
+    const unsigned long long w = ((unsigned long long)sx.epoch << 32) | (unsigned long long)__float_as_uint(sk);
+    for (int g = 0; g < sx.world; ++g) sel_st_relaxed_sys64(sx.thr_x[g] + (size_t)sx.rank * sx.b_cap + q, w);
+}
+// Lane g < world waits for shard g's word of query q; returns the min over shards on every lane of the warp.
+// Bounded spin: a dead peer must not hang the GPU (-inf = admit everything, and the error flag is raised).
+__device__ __forceinline__ float sel_wait_global_kth(const SelExchange& sx, long long q, int lane) {
+    float v = __int_as_float(0x7f800000);
+    if (lane < sx.world) {
+        const unsigned long long* slot = sx.thr_x[sx.rank] + (size_t)lane * sx.b_cap + q;
+        const long long t0 = clock64();
+        unsigned long long w = sel_ld_acquire_sys64(slot);
+        while ((int)((unsigned int)(w >> 32) - sx.epoch) < 0) {
+            if (clock64() - t0 > 6000000000ll) { atomicExch(sx.flags + 17, 1u); w = 0xff800000ull; break; }
+            __nanosleep(64);
+            w = sel_ld_acquire_sys64(slot);
+        }
+        v = __uint_as_float((unsigned int)w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
 // K-th largest key prefix by radix select (4 passes x 8 bits over the order-preserving score image), then an
@@ -92,11 +107,10 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
     extern __shared__ unsigned long long keys[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sel_prefix, sel_remaining, kept_s, valid_s;
+    __shared__ float global_kth_s;
     const int q = blockIdx.x;
-    if (sx.mode == kSelCompactMin) {
-        if ((int)threadIdx.x < sx.world) sel_wait_shard(sx, threadIdx.x);
-        __syncthreads();
-    }
+    const bool shared = sx.mode == kSelShared;
+    if (shared) K = sx.k_share;                       // what this shard publishes: its ceil(k / G)-th best
     unsigned int c_raw = fixed_count >= 0 ? (unsigned int)fixed_count : cnt[q];
     if (c_raw > cap) {
         if (threadIdx.x == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
@@ -116,14 +130,8 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
     if (lane_id() == 0 && nvalid) atomicAdd(&valid_s, nvalid);
     __syncthreads();
     float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
-    if (sx.mode == kSelCompactMin) {
-        const float sk = sel_global_kth(sx, sx.q0 + q);          // lower bound of the global K-th best score
-        if (sk > __int_as_float(0xff800000)) {
-            const float m = margin ? margin[q] : 0.0f;
-            t = sk - m;
-            if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);
-        }
-    } else if ((int)valid_s >= K) {
+    float sk = t;                           // the K-th best score of the list
+    if ((int)valid_s >= K) {
         unsigned int mask = 0u;
         for (int shift = 24; shift >= 0; shift -= 8) {
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
@@ -166,15 +174,21 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
             mask |= 255u << shift;
             __syncthreads();
         }
-        const float sk = ordered_to_f32(sel_prefix);
+        sk = ordered_to_f32(sel_prefix);
+    }
+    if (shared) {                                     // publish first, then wait: no shard ever waits on a waiter
+        if (threadIdx.x == 0) sel_publish_kth(sx, sx.q0 + q, sk);       // -inf = "cannot bound yet"
+        if (threadIdx.x < 32) {
+            const float g = sel_wait_global_kth(sx, sx.q0 + q, threadIdx.x);
+            if (threadIdx.x == 0) global_kth_s = g;
+        }
+        __syncthreads();
+        sk = global_kth_s;                            // lower bound of the global k-th best score
+    }
+    if (sk > __int_as_float(0xff800000)) {
         const float m = margin ? margin[q] : 0.0f;
         t = sk - m;
         if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
-        if (sx.mode == kSelKthToPeers) t = sk;
-    }
-    if (sx.mode == kSelKthToPeers) {                  // K here is ceil(k / shards); -inf = "cannot bound yet"
-        if (threadIdx.x == 0) sel_publish_kth(sx, sx.q0 + q, t);
-        return;
     }
     for (int base = 0; base < c; base += blockDim.x) {
         const int i = base + threadIdx.x;
@@ -202,7 +216,7 @@ constexpr int kSelWarpKeys = 1024;          // keys staged per warp (8 KB); long
 
 __global__ void __launch_bounds__(kSelWarps * 32)
 select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap,
-                           int B, int K, const float* __restrict__ margin, float* __restrict__ thr,
+                           int B, int K, int fixed_count, const float* __restrict__ margin, float* __restrict__ thr,
                            unsigned int* needed_cap, unsigned int* __restrict__ ovf,
                            const __grid_constant__ SelExchange sx) {
     __shared__ unsigned long long keys_all[kSelWarps][kSelWarpKeys];
@@ -210,12 +224,10 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int q = blockIdx.x * kSelWarps + w;
     if (q >= B) return;
-    if (sx.mode == kSelCompactMin) {
-        if (l < sx.world) sel_wait_shard(sx, l);
-        __syncwarp();
-    }
+    const bool shared = sx.mode == kSelShared;
+    if (shared) K = sx.k_share;                       // what this shard publishes: its ceil(k / G)-th best
     unsigned int* hist = hist_all[w];
-    unsigned int c_raw = cnt[q];
+    unsigned int c_raw = fixed_count >= 0 ? (unsigned int)fixed_count : cnt[q];
     if (c_raw > cap) {
         if (l == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
         c_raw = cap;
@@ -234,14 +246,8 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
     __syncwarp();
     for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
     float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
-    if (sx.mode == kSelCompactMin) {
-        const float sk = sel_global_kth(sx, sx.q0 + q);          // lower bound of the global K-th best score
-        if (sk > __int_as_float(0xff800000)) {
-            const float m = margin ? margin[q] : 0.0f;
-            t = sk - m;
-            if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);
-        }
-    } else if ((int)nvalid >= K) {
+    float sk = t;                           // the K-th best score of the list
+    if ((int)nvalid >= K) {
         unsigned int mask = 0u, prefix = 0u, remaining = (unsigned int)K;
         for (int shift = 24; shift >= 0; shift -= 8) {
 #pragma unroll
@@ -285,15 +291,17 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
             mask |= 255u << shift;
             __syncwarp();
         }
-        const float sk = ordered_to_f32(prefix);
+        sk = ordered_to_f32(prefix);
+    }
+    if (shared) {                                     // publish first, then wait: no shard ever waits on a waiter
+        if (l == 0) sel_publish_kth(sx, sx.q0 + q, sk);                 // -inf = "cannot bound yet"
+        __syncwarp();
+        sk = sel_wait_global_kth(sx, sx.q0 + q, l);   // lower bound of the global k-th best score
+    }
+    if (sk > __int_as_float(0xff800000)) {
         const float m = margin ? margin[q] : 0.0f;
         t = sk - m;
         if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
-        if (sx.mode == kSelKthToPeers) t = sk;
-    }
-    if (sx.mode == kSelKthToPeers) {                  // K here is ceil(k / shards); -inf = "cannot bound yet"
-        if (l == 0) sel_publish_kth(sx, sx.q0 + q, t);
-        return;
     }
     unsigned int kept = 0u;
     for (int base = 0; base < c; base += 32) {
@@ -344,15 +352,50 @@ __device__ __forceinline__ void exact_dot2_v4(const float* __restrict__ xa, cons
     sb = warp_sum(sb);
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(kFinalThreads, 2)      // two CTAs (32 warps) per SM: the row gathers are latency-bound
+// Four candidates in flight per warp (the small-list variant of final_kernel runs four warps per CTA): per
+// candidate the same fma sequence as exact_dot2_v4, so the sums are bit-identical whichever variant scores a row.
+__device__ __forceinline__ void exact_dot4_v4(const float* __restrict__ x0, const float* __restrict__ x1,
+                                              const float* __restrict__ x2, const float* __restrict__ x3,
+                                              const float4 (&qreg)[4], int nblk, double (&s)[4]) {
+    s[0] = s[1] = s[2] = s[3] = 0.0;
+    const int l = lane_id();
+#pragma unroll 1
+    for (int b = 0; b < nblk; ++b) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(x0) + b * 32 + l);
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(x1) + b * 32 + l);
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(x2) + b * 32 + l);
+        const float4 a3 = __ldg(reinterpret_cast<const float4*>(x3) + b * 32 + l);
+        const float4 q = b == 0 ? qreg[0] : (b == 1 ? qreg[1] : (b == 2 ? qreg[2] : qreg[3]));
+        s[0] = fma((double)a0.x, (double)q.x, s[0]); s[1] = fma((double)a1.x, (double)q.x, s[1]);
+        s[2] = fma((double)a2.x, (double)q.x, s[2]); s[3] = fma((double)a3.x, (double)q.x, s[3]);
+        s[0] = fma((double)a0.y, (double)q.y, s[0]); s[1] = fma((double)a1.y, (double)q.y, s[1]);
+        s[2] = fma((double)a2.y, (double)q.y, s[2]); s[3] = fma((double)a3.y, (double)q.y, s[3]);
+        s[0] = fma((double)a0.z, (double)q.z, s[0]); s[1] = fma((double)a1.z, (double)q.z, s[1]);
+        s[2] = fma((double)a2.z, (double)q.z, s[2]); s[3] = fma((double)a3.z, (double)q.z, s[3]);
+        s[0] = fma((double)a0.w, (double)q.w, s[0]); s[1] = fma((double)a1.w, (double)q.w, s[1]);
+        s[2] = fma((double)a2.w, (double)q.w, s[2]); s[3] = fma((double)a3.w, (double)q.w, s[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = warp_sum(s[j]);
+}
+
+// Two launch shapes share this kernel.  SMALL: 128 threads, a list of at most `small_keys` survivors sorted in
+// 12-24 KB of shared memory, six CTAs per SM -- the normal case (about 1.5 k survivors per query), where a
+// 512-thread CTA with shared memory for a full-capacity list spent its time in barriers and left the row gathers
+// (random 512-byte reads, latency-bound) with too little in flight.  BIG: the full-capacity shape, launched behind
+// the small one for the queries it skipped (heavily tied lists); it exits at once for everyone else.
+template <bool EXACT, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? kFinalSmallThreads : kFinalThreads, SMALL ? 6 : 2)
 final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned int cap,
              int K, const float* __restrict__ table, int d, const float* __restrict__ queries, long long idx_offset,
              long long* __restrict__ out_idx, float* __restrict__ out_score, double* __restrict__ out_score64,
-             unsigned int* needed_cap, unsigned int* __restrict__ ovf, const __grid_constant__ PeerDst peer) {
+             unsigned int* needed_cap, unsigned int* __restrict__ ovf, int small_keys,
+             const __grid_constant__ PeerDst peer) {
     extern __shared__ unsigned long long sm[];
     const int q = blockIdx.x;
     unsigned int c_raw = cnt[q];
+    // which of the two launches owns this query (small_keys == 0: there is only one launch)
+    if (small_keys > 0 && ((c_raw > (unsigned int)small_keys) == SMALL)) return;
     if (c_raw > cap) {
         if (threadIdx.x == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
         c_raw = cap;
@@ -375,7 +418,28 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
 #pragma unroll
             for (int b = 0; b < 4; ++b)
                 qreg[b] = b < nblk ? __ldg(reinterpret_cast<const float4*>(qv) + b * 32 + lane_id()) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = 2 * warp; i < c; i += 2 * nwarps) {
+            for (int i = 4 * warp; SMALL && i < c; i += 4 * nwarps) {
+                unsigned long long kx[4];
+                const float* xp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    kx[j] = (i + j < c) ? list[i + j] : 0ull;
+                    xp[j] = table + (size_t)(kx[j] != 0ull ? key_row(kx[j]) : 0u) * d;
+                }
+                double sx[4];
+                exact_dot4_v4(xp[0], xp[1], xp[2], xp[3], qreg, nblk, sx);
+                if (lane_id() == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (i + j < c) {
+                            const bool ok = kx[j] != 0ull && sx[j] == sx[j];
+                            sk[i + j] = ok ? f64_to_ordered(sx[j]) : 0ull;
+                            rw[i + j] = ok ? key_row(kx[j]) : 0xffffffffu;
+                        }
+                    }
+                }
+            }
+            for (int i = 2 * warp; !SMALL && i < c; i += 2 * nwarps) {
                 const unsigned long long ka = list[i];
                 const unsigned long long kb = (i + 1 < c) ? list[i + 1] : 0ull;
                 const uint32_t ra = key_row(ka), rb = key_row(kb);
@@ -445,6 +509,157 @@ final_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __
             out_score[o] = __int_as_float(0xff800000);
             if (out_score64) out_score64[o] = -INFINITY;
         }
+        if (overflowed && i == 0) out_idx[o] = -2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// final, ONE WARP per query: the shape for the normal case (k <= 512, a few hundred survivors per query).  A CTA per
+// query spends its life in barriers (list load -> gathers -> 36-phase bitonic sort -> store) with at most six
+// queries in flight per SM; a warp per query needs no barrier at all, ~48 queries per SM are in flight at once, and
+// the whole batch finishes in about the latency of one query.  Eight row gathers are in flight per warp; per
+// candidate the fma sequence is that of exact_dot2_v4 / exact_dot, so every final shape returns the same bits.
+constexpr int kFinalWarpQ = 4;          // warps (queries) per CTA
+constexpr int kFinalWarpKeys = 1024;    // longest list a warp sorts (12 KB of shared memory per warp)
+
+template <int NC>
+__device__ __forceinline__ void exact_dotn_v4(const float* const (&x)[NC], const float4 (&qreg)[4], int nblk,
+                                              double (&s)[NC]) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s[j] = 0.0;
+    const int l = lane_id();
+#pragma unroll 1
+    for (int b = 0; b < nblk; ++b) {
+        float4 a[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) a[j] = __ldg(reinterpret_cast<const float4*>(x[j]) + b * 32 + l);
+        const float4 q = b == 0 ? qreg[0] : (b == 1 ? qreg[1] : (b == 2 ? qreg[2] : qreg[3]));
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            s[j] = fma((double)a[j].x, (double)q.x, s[j]);
+            s[j] = fma((double)a[j].y, (double)q.y, s[j]);
+            s[j] = fma((double)a[j].z, (double)q.z, s[j]);
+            s[j] = fma((double)a[j].w, (double)q.w, s[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s[j] = warp_sum(s[j]);
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kFinalWarpQ * 32, 4)
+final_warp_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned int cap,
+                  int B, int K, const float* __restrict__ table, int d, const float* __restrict__ queries,
+                  long long idx_offset, long long* __restrict__ out_idx, float* __restrict__ out_score,
+                  double* __restrict__ out_score64, unsigned int* needed_cap, unsigned int* __restrict__ ovf,
+                  const __grid_constant__ PeerDst peer) {
+    __shared__ unsigned long long sk_all[kFinalWarpQ][kFinalWarpKeys];
+    __shared__ uint32_t rw_all[kFinalWarpQ][kFinalWarpKeys];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int q = blockIdx.x * kFinalWarpQ + w;
+    if (q >= B) return;
+    unsigned int c_raw = cnt[q];
+    // longer lists belong to final_kernel<EXACT, false>, launched behind this kernel whenever the capacity allows them
+    if (c_raw > (unsigned int)kFinalWarpKeys && cap > (unsigned int)kFinalWarpKeys) return;
+    if (c_raw > cap) {
+        if (l == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
+        c_raw = cap;
+        __syncwarp();
+    }
+    const int c = (int)c_raw;
+    const int P = next_pow2(c > 1 ? c : 2);
+    unsigned long long* sk = sk_all[w];
+    uint32_t* rw = rw_all[w];
+    const unsigned long long* list = cand + (size_t)q * cap;
+    if (EXACT) {
+        const float* qv = queries + (size_t)q * d;
+        const bool vec = (d % 128 == 0) && d <= 512 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(qv)) & 15u) == 0;
+        if (vec) {
+            float4 qreg[4];
+            const int nblk = d / 128;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                qreg[b] = b < nblk ? __ldg(reinterpret_cast<const float4*>(qv) + b * 32 + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < c; i += 8) {
+                // lane j < 8 fetches key i + j; everyone learns the eight rows by shuffle
+                const unsigned long long mine = (l < 8 && i + l < c) ? list[i + l] : 0ull;
+                unsigned long long kx[8];
+                const float* xp[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    kx[j] = __shfl_sync(0xffffffffu, mine, j);
+                    xp[j] = table + (size_t)(kx[j] != 0ull ? key_row(kx[j]) : 0u) * d;
+                }
+                double sx[8];
+                exact_dotn_v4<8>(xp, qreg, nblk, sx);
+                if (l < 8 && i + l < c) {
+                    double sv = sx[0];
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) sv = l == j ? sx[j] : sv;
+                    const bool ok = mine != 0ull && sv == sv;
+                    sk[i + l] = ok ? f64_to_ordered(sv) : 0ull;
+                    rw[i + l] = ok ? key_row(mine) : 0xffffffffu;
+                }
+            }
+        } else {
+            for (int i = 0; i < c; ++i) {
+                const unsigned long long k = list[i];
+                const uint32_t row = key_row(k);
+                const double sv = (k != 0ull) ? exact_dot(table + (size_t)row * d, qv, d) : 0.0;
+                if (l == 0) {
+                    sk[i] = (k != 0ull && sv == sv) ? f64_to_ordered(sv) : 0ull;
+                    rw[i] = (k != 0ull && sv == sv) ? row : 0xffffffffu;
+                }
+            }
+        }
+        for (int i = c + l; i < P; i += 32) { sk[i] = 0ull; rw[i] = 0xffffffffu; }
+    } else {
+        for (int i = l; i < P; i += 32) {
+            const unsigned long long k = (i < c) ? list[i] : 0ull;
+            sk[i] = k >> 32;
+            rw[i] = (k != 0ull) ? key_row(k) : 0xffffffffu;
+        }
+    }
+    __syncwarp();
+    // descending bitonic sort by (score, then row ascending) -- one warp, no block barrier
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = l; i < P; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool i_first = sk[i] > sk[ixj] || (sk[i] == sk[ixj] && rw[i] < rw[ixj]);
+                    if (((i & kk) == 0) ? !i_first : i_first) {
+                        const unsigned long long t = sk[i]; sk[i] = sk[ixj]; sk[ixj] = t;
+                        const uint32_t r = rw[i]; rw[i] = rw[ixj]; rw[ixj] = r;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    const bool overflowed = ovf[q] != 0u || cnt[q] > cap;
+    if (peer.world > 0) {
+        // sharded catalogue: straight into the exchange buffer of the GPU that merges this query (see final_kernel)
+        const long long qg = peer.q0 + q;
+        const int owner = (int)(qg / peer.q_per_owner);
+        const size_t o = ((size_t)peer.rank * peer.q_cap + (size_t)(qg - (long long)owner * peer.q_per_owner)) * peer.k_cap;
+        double* xs = peer.xs[owner] + o;
+        long long* xi = peer.xi[owner] + o;
+        for (int i = l; i < K; i += 32) {
+            const bool ok = i < c && rw[i] != 0xffffffffu;
+            const double sv = EXACT ? ordered_to_f64(sk[i]) : (double)ordered_to_f32((uint32_t)sk[i]);
+            xs[i] = ok ? sv : -INFINITY;
+            xi[i] = ok ? (long long)rw[i] + idx_offset : -1;
+        }
+        return;
+    }
+    for (int i = l; i < K; i += 32) {
+        const size_t o = (size_t)q * K + i;
+        const bool ok = i < c && rw[i] != 0xffffffffu;
+        const double sv = ok ? (EXACT ? ordered_to_f64(sk[i]) : (double)ordered_to_f32((uint32_t)sk[i])) : -INFINITY;
+        out_idx[o] = ok ? (long long)rw[i] + idx_offset : -1;
+        out_score[o] = (float)sv;
+        if (out_score64) out_score64[o] = sv;
         if (overflowed && i == 0) out_idx[o] = -2;
     }
 }
@@ -550,13 +765,15 @@ inline size_t pow2_ge(size_t v) {
 
 cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, unsigned int cap, int B, int K,
                                   int fixed_count, const float* margin, float* thr, unsigned int* needed_cap,
-                                  unsigned int* ovf, const SelExchange* sxp, cudaStream_t stream) {
+                                  unsigned int* ovf, const SelExchange* sxp, int dense_warp, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     SelExchange sx;
     if (sxp) sx = *sxp; else memset(&sx, 0, sizeof sx);
-    if (fixed_count < 0 && B >= 128) {      // filter rounds of large batches: short lists, one warp per query
+    // large batches: one warp per query -- the short lists of the filter rounds, and (dense_warp) the dense round's
+    // too: thousands of independent warps re-reading a 32 KB list through L2 beat a CTA per query in barriers
+    if (B >= 128 && (fixed_count < 0 || dense_warp)) {
         select_compact_warp_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(
-            cand, cnt, cap, B, K, margin, thr, needed_cap, ovf, sx);
+            cand, cnt, cap, B, K, fixed_count, margin, thr, needed_cap, ovf, sx);
         return cudaGetLastError();
     }
     // stage only what can be there: a dense round holds fixed_count keys, a filter round at most cap
@@ -572,23 +789,60 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
 cudaError_t launch_final(const unsigned long long* cand, const unsigned int* cnt, unsigned int cap, int B, int K,
                          int exact, const float* table, int d, const float* queries, long long idx_offset,
                          long long* out_idx, float* out_score, double* out_score64, unsigned int* needed_cap,
-                         unsigned int* ovf, const PeerDst* peer, cudaStream_t stream) {
+                         unsigned int* ovf, const PeerDst* peer, int allow_small, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    const size_t smem = pow2_ge(cap) * (sizeof(unsigned long long) + sizeof(uint32_t));
     PeerDst pd;
     if (peer) pd = *peer; else memset(&pd, 0, sizeof pd);
+    const size_t per_key = sizeof(unsigned long long) + sizeof(uint32_t);
+    // lists of up to small_keys survivors (the normal case) go to the small shape; if that already covers the
+    // capacity it is the only launch
+    size_t small_keys = pow2_ge((size_t)(2 * K > 1024 ? 2 * K : 1024));
+    const bool only_small = small_keys >= pow2_ge(cap);
+    if (only_small) small_keys = pow2_ge(cap);
+    const size_t smem_small = small_keys * per_key, smem_big = pow2_ge(cap) * per_key;
+    const bool use_small = allow_small && smem_small <= 24 * 1024;
     cudaError_t e;
-    if (exact) {
-        e = set_smem(final_kernel<true>, smem);
-        if (e != cudaSuccess) return e;
-        final_kernel<true><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset, out_idx,
-                                                            out_score, out_score64, needed_cap, ovf, pd);
-    } else {
-        e = set_smem(final_kernel<false>, smem);
-        if (e != cudaSuccess) return e;
-        final_kernel<false><<<B, kFinalThreads, smem, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
-                                                             out_idx, out_score, out_score64, needed_cap, ovf, pd);
+    if (allow_small == 1 && 2 * K <= kFinalWarpKeys) {
+        // the normal case: a warp per query for lists of up to kFinalWarpKeys survivors, then the full-capacity CTA
+        // shape for whatever is longer (it exits at once for every query the warp kernel answered)
+        const int grid = (B + kFinalWarpQ - 1) / kFinalWarpQ;
+        if (exact)
+            final_warp_kernel<true><<<grid, kFinalWarpQ * 32, 0, stream>>>(cand, cnt, cap, B, K, table, d, queries, idx_offset,
+                                                                        out_idx, out_score, out_score64, needed_cap, ovf, pd);
+        else
+            final_warp_kernel<false><<<grid, kFinalWarpQ * 32, 0, stream>>>(cand, cnt, cap, B, K, table, d, queries, idx_offset,
+                                                                         out_idx, out_score, out_score64, needed_cap, ovf, pd);
+        if (cap <= (unsigned int)kFinalWarpKeys) return cudaGetLastError();      // no list can be longer
+        const int skip = kFinalWarpKeys < (int)cap ? kFinalWarpKeys : (int)cap;
+        if (exact) {
+            e = set_smem(final_kernel<true, false>, smem_big);
+            if (e != cudaSuccess) return e;
+            final_kernel<true, false><<<B, kFinalThreads, smem_big, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
+                                                                           out_idx, out_score, out_score64, needed_cap, ovf, skip, pd);
+        } else {
+            e = set_smem(final_kernel<false, false>, smem_big);
+            if (e != cudaSuccess) return e;
+            final_kernel<false, false><<<B, kFinalThreads, smem_big, stream>>>(cand, cnt, cap, K, table, d, queries, idx_offset,
+                                                                            out_idx, out_score, out_score64, needed_cap, ovf, skip, pd);
+        }
+        return cudaGetLastError();
     }
+#define HWER_LAUNCH_FINAL(EX)                                                                                          \
+    do {                                                                                                               \
+        if (use_small) {                                                                                               \
+            final_kernel<EX, true><<<B, kFinalSmallThreads, smem_small, stream>>>(                                     \
+                cand, cnt, cap, K, table, d, queries, idx_offset, out_idx, out_score, out_score64, needed_cap, ovf,   \
+                only_small ? 0 : (int)small_keys, pd);                                                                 \
+            if (only_small) break;                                                                                     \
+        }                                                                                                              \
+        e = set_smem(final_kernel<EX, false>, smem_big);                                                               \
+        if (e != cudaSuccess) return e;                                                                                \
+        final_kernel<EX, false><<<B, kFinalThreads, smem_big, stream>>>(                                               \
+            cand, cnt, cap, K, table, d, queries, idx_offset, out_idx, out_score, out_score64, needed_cap, ovf,       \
+            use_small ? (int)small_keys : 0, pd);                                                                      \
+    } while (0)
+    if (exact) HWER_LAUNCH_FINAL(true); else HWER_LAUNCH_FINAL(false);
+#undef HWER_LAUNCH_FINAL
     return cudaGetLastError();
 }
 

@@ -226,6 +226,15 @@ class TopKIndex:
                                               ctypes.byref(ol)))
         return ms.value, fl.value, ol.value
 
+    STAGES = ("filter", "select", "final", "exchange")
+
+    def profile_stages(self):
+        """{stage: summed ms} of the bracketed launches since the last profile_read (call before it)."""
+        buf = (ctypes.c_double * 4)()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().hwer_profile_stages(self._h, _stream(self.device), buf))
+        return dict(zip(self.STAGES, [buf[i] for i in range(4)]))
+
     def profile_launches(self, cap=4096):
         """Durations (ms) of the score-filter launches since the last profile_read, in launch order."""
         buf = (ctypes.c_double * cap)()

@@ -36,6 +36,7 @@ class Node:
         self.node_external_id = str(node_external_id)
         self._pair = (self.node_type, self.node_external_id)
         self._pair_hash = hash(self._pair)
+        self._hint = (0, -1)       # (token of the NodeIndex that placed this object, its row): see NodeIndex.rows_of
 
     def __hash__(self):
         return self._pair_hash
@@ -49,12 +50,14 @@ class Node:
         # string hashes are per process (PYTHONHASHSEED): never carry the cached hash across a pickle
         state = dict(self.__dict__)
         state.pop("_pair_hash", None)
+        state.pop("_hint", None)          # index tokens are per process too
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._pair = (self.node_type, self.node_external_id)
         self._pair_hash = hash(self._pair)
+        self._hint = (0, -1)
 
     def __repr__(self):
         return str(self._pair)
@@ -88,17 +91,108 @@ class Edge:
         return "{src: %s, dst: %s, weight: %s}" % (self.src, self.dst, self.weight)
 
 
+class _InverseView:
+    """row -> Node over a NodeIndex: a dict for the nodes that were added as objects, arithmetic for node ranges."""
+
+    def __init__(self, index):
+        self._index = index
+        self._objects = {v: k for k, v in dict.items(index)}
+
+    def __getitem__(self, row):
+        n = self._objects.get(row)
+        if n is not None:
+            return n
+        for node_type, first_row, count in self._index._ranges:
+            if first_row <= row < first_row + count:
+                return Node(node_type, row - first_row)
+        raise KeyError(row)
+
+    def __len__(self):
+        return len(self._index)
+
+
 class NodeIndex(dict):
-    """Node -> global row, with the `.inverse` view the reference gets from bidict (row -> Node)."""
+    """Node -> global row, with the `.inverse` view the reference gets from bidict (row -> Node).
+
+    Catalogues of tens of millions of nodes do not need a Python object per node: `add_range(node_type, count)`
+    registers `count` nodes of one type whose external ids are 0 .. count-1 on consecutive rows; lookups of such
+    nodes are arithmetic.  Everything else (nodes added as objects) is an ordinary dict entry."""
+
+    _tokens = iter(range(1, 1 << 62))
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         self._inverse = None
+        self._ranges = []            # (node_type, first_row, count)
+        self._range_total = 0
+        self._token = next(NodeIndex._tokens)
+
+    def place(self, nodes, first_row):
+        """Adds `nodes` on consecutive rows and leaves each object a hint of where it lives, so that looking the SAME
+        objects up again (the anchors of a batched query are usually the objects the model was fitted with) costs an
+        attribute read instead of a hash + equality call per node."""
+        tok = self._token
+        for i, n in enumerate(nodes, first_row):
+            dict.__setitem__(self, n, i)
+            n._hint = (tok, i)
+        self._inverse = None
+
+    def rows_of(self, nodes):
+        """Rows of `nodes` as a list (-1 = unknown node)."""
+        tok, get = self._token, self.get
+        return [n._hint[1] if n._hint[0] == tok else get(n, -1) for n in nodes]
+
+    def add_range(self, node_type, count):
+        first = len(self)
+        self._ranges.append((str(node_type), first, int(count)))
+        self._range_total += int(count)
+        self._inverse = None
+        return first
+
+    def _range_row(self, node):
+        if not self._ranges or not isinstance(node, Node):
+            return None
+        ext = node.node_external_id
+        if not ext.isdigit() or (len(ext) > 1 and ext[0] == "0"):
+            return None
+        i = int(ext)
+        for node_type, first_row, count in self._ranges:
+            if node.node_type == node_type and i < count:
+                return first_row + i
+        return None
+
+    def __len__(self):
+        return dict.__len__(self) + self._range_total
+
+    def __contains__(self, node):
+        return dict.__contains__(self, node) or self._range_row(node) is not None
+
+    def __missing__(self, node):                 # dict.__getitem__ falls through to here
+        row = self._range_row(node)
+        if row is None:
+            raise KeyError(node)
+        return row
+
+    def get(self, node, default=None):
+        row = dict.get(self, node)
+        if row is None:
+            row = self._range_row(node)
+        return default if row is None else row
+
+    def rows_by_type(self):
+        """{node_type: ascending numpy array of that type's global rows}."""
+        by_type = defaultdict(list)
+        for n, i in dict.items(self):
+            by_type[n.node_type].append(i)
+        out = {t: [np.asarray(r, dtype=np.int64)] for t, r in by_type.items()}
+        for node_type, first_row, count in self._ranges:
+            out.setdefault(node_type, []).append(np.arange(first_row, first_row + count, dtype=np.int64))
+        return {t: np.sort(np.concatenate(parts)) for t, parts in out.items()}
 
     @property
     def inverse(self):
         if self._inverse is None or len(self._inverse) != len(self):
-            self._inverse = {v: k for k, v in self.items()}
+            self._inverse = _InverseView(self)
         return self._inverse
 
     def __setitem__(self, key, value):
@@ -129,9 +223,12 @@ class MultiKNN:
         self.mode = mode
         assert len(nodes_to_idx) == len(vectors)
         self.table = _as_device_table(vectors, self.device)
-        rows_by_type: Dict[str, List[int]] = defaultdict(list)
-        for n, i in nodes_to_idx.items():
-            rows_by_type[n.node_type].append(i)
+        if isinstance(nodes_to_idx, NodeIndex):
+            rows_by_type = nodes_to_idx.rows_by_type()
+        else:
+            rows_by_type: Dict[str, List[int]] = defaultdict(list)
+            for n, i in nodes_to_idx.items():
+                rows_by_type[n.node_type].append(i)
         self.idxs: Dict[str, np.ndarray] = {}
         self.idxs_dev: Dict[str, torch.Tensor] = {}
         self.offset: Dict[str, int] = {}
@@ -189,12 +286,17 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         self.mode = mode               # "exact" (fp64-rescored, the reference's result) or "bf16"
         self.log = getLogger(type(self).__name__)
 
+    def add_node_range(self, node_type: str, count: int):
+        """`count` nodes of `node_type` with external ids 0 .. count-1 on the next `count` rows, without a Python
+        object per node (catalogues of tens of millions of items).  Returns the first row."""
+        assert node_type in self.node_types
+        return self.nodes_to_idx.add_range(node_type, count)
+
     def add_nodes(self, nodes: List[Node]):
         assert len(set(nodes)) == len(nodes)
-        assert self.nodes_to_idx.keys().isdisjoint(set(nodes))
+        assert not any(n in self.nodes_to_idx for n in nodes)
         assert len(set([n.node_type for n in nodes]) - self.node_types) == 0
-        all_count = len(self.nodes_to_idx)
-        self.nodes_to_idx.update(zip(nodes, range(all_count, all_count + len(nodes))))
+        self.nodes_to_idx.place(nodes, len(self.nodes_to_idx))
         return self
 
     def __build_knn__(self, vectors, shadow=None):
@@ -227,8 +329,7 @@ class RecommendationBase(metaclass=abc.ABCMeta):
 
     # ------------------------------------------------------------------ pair scores
     def _rows_of(self, nodes) -> torch.Tensor:
-        idx = [self.nodes_to_idx[n] if n in self.nodes_to_idx else -1 for n in nodes]
-        return torch.tensor(idx, dtype=torch.int64, device=self.device_vectors.device)
+        return torch.tensor(self.nodes_to_idx.rows_of(nodes), dtype=torch.int64, device=self.device_vectors.device)
 
     def predict_rows(self, src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
         return ops.pair_score(self.device_vectors, src_rows, dst_rows)
@@ -302,7 +403,7 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         NOT the composed query's score -- each anchor's list sorted descending (stable)."""
         return ops.rerank(self.device_vectors, rows, "pair", anchor_rows=anchor_rows)
 
-    def find_closest_neighbours_batch(self, node_type: str, anchors: List[Node], k=200,
+    def find_closest_neighbours_batch(self, node_type: str, anchors, k=200,
                                       positive: List[List[Node]] = None, negative: List[List[Node]] = None
                                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """One search for all anchors (the loop of validation.model_get_topk_knn, hwer/validation.py:30-35).
@@ -310,11 +411,17 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         convention as find_closest_neighbours(node_type, anchor, positive[i], negative[i], k) called per anchor."""
         assert self.fit_done
         assert node_type in self.node_types and node_type in self.knn.knn
-        for a in anchors:
-            if a not in self.nodes_to_idx:
-                raise NodeNotFoundException("Node = %s, was not provided in training" % a)
-        anchor_rows = self._rows_of(anchors)
-        queries = self._query_embeddings(anchors, positive, negative)
+        if isinstance(anchors, torch.Tensor):
+            # anchors already resolved to global rows (a serving tier that keeps its own id map): int64, any device
+            anchor_rows = anchors.to(device=self.device_vectors.device, dtype=torch.int64, non_blocking=True)
+        else:
+            rows = self.nodes_to_idx.rows_of(anchors)
+            if rows and min(rows) < 0:
+                raise NodeNotFoundException("Node = %s, was not provided in training" % anchors[rows.index(min(rows))])
+            anchor_rows = torch.tensor(rows, dtype=torch.int64, device=self.device_vectors.device)
+        pos = self._csr_rows(positive) if positive is not None and any(positive) else None
+        neg = self._csr_rows(negative) if negative is not None and any(negative) else None
+        queries = ops.compose_queries(self.device_vectors, anchor_rows, pos, neg)
         rows, _ = self.knn.query_batch(queries, node_type, k=k)
         return self._batch_scores(anchor_rows, queries, rows)
 

@@ -165,16 +165,19 @@ class ShardedTopK:
             cap = 0
             for _ in range(6):
                 idx, score, _ = self.topk_p2p_async(queries, k, mode, cap=cap)
+                # one stream synchronisation per step: the largest capacity demand of ANY rank and a peer timeout
+                # come back through the exchange buffers (csrc/exchange.cu), so every rank takes the same decision
+                # here without a host-side collective
                 rc, need = self.index.finish()
-                # an overflow on ANY rank re-runs the collective everywhere with the largest capacity asked for
-                t = torch.tensor([need if rc == N.HWER_E_OVERFLOW else 0], dtype=torch.int64, device=queries.device)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-                if rc not in (N.HWER_OK, N.HWER_E_OVERFLOW):
-                    N.check(rc)
-                cap = int(t.item())
-                if cap == 0:
-                    self._px.check()
+                if rc == N.HWER_OK:
                     return idx, score
+                if rc != N.HWER_E_OVERFLOW:
+                    N.check(rc)
+                if need > ops.TopKIndex.MAX_CAP:
+                    raise N.HwerError(N.HWER_E_OVERFLOW, "a query needs a candidate list of %d rows (more than %d rows "
+                                      "inside the bf16 margin of its k-th score): answer it with "
+                                      "TopKIndex.topk_exhaustive on every shard and merge" % (need, ops.TopKIndex.MAX_CAP))
+                cap = need
             raise N.HwerError(N.HWER_E_OVERFLOW, "candidate lists kept overflowing")
         idx, s64 = self.local_topk(queries, k, mode)
         if not multi:

@@ -113,6 +113,11 @@ int hwer_topk_exhaustive(hwer_index_t* index, const float* queries_dev, int32_t 
 int hwer_profile(hwer_index_t* index, int enable);
 int hwer_profile_read(hwer_index_t* index, void* stream, double* filter_ms, int64_t* filter_launches,
                       int64_t* other_launches);
+/* Where a step's time goes: summed durations (ms) since the last hwer_profile_read of the brackets around
+ * [0] the score-filter launches (+ spill extract), [1] the select launches (incl. waits on peer thresholds),
+ * [2] the final re-score + sort, [3] the peer exchange (signal, owner merge, collect).  Call BEFORE
+ * hwer_profile_read, which resets the events. */
+int hwer_profile_stages(hwer_index_t* index, void* stream, double* out4_ms);
 /* Per-launch view of the same events (call BEFORE hwer_profile_read, which resets them): the durations, in launch
  * order, of the score-filter launches since the last read.  *n_out = number of launches recorded; at most `cap`
  * are written to out_ms (milliseconds). */
@@ -161,6 +166,9 @@ int hwer_topk_sharded(hwer_index_t* index, hwer_exchange_t* exchange, const floa
                       double* out_score64_dev, int32_t phases, void* stream);
 /* Synchronises `stream`; HWER_E_PEER if any wait on a peer timed out since the exchange was created. */
 int hwer_exchange_error(hwer_exchange_t* exchange, void* stream);
+/* hwer_topk_finish after hwer_topk_sharded reports the outcome of the COLLECTIVE: the capacity demand is the largest
+ * over all ranks (it travels with the exchange flags, so every rank takes the same retry decision without a
+ * host-side collective) and a peer timeout on this rank surfaces as HWER_E_PEER. */
 
 /* out[p] = (dot(row src[p], row dst[p]) + 1) / 2; a row id outside [0, n) means "node not seen in training"
  * and scores with clip(row 0, 1e-6, 1e-5).

@@ -42,6 +42,7 @@ def main():
                     os.environ.pop(v, None)
                 else:
                     os.environ[v] = str(val)
+            index = hw.ops.TopKIndex(table, shadow, max_norm=1.0001)   # the knobs are read when an index is created
             try:
                 for _ in range(3):
                     idx = index.topk(q, a.k)[0]

@@ -629,6 +629,33 @@ def test_gcn_ncf_rerank_matches_reference(hw, golden_ncf):
     np.testing.assert_allclose(sc.cpu().numpy(), g["fcn_score"], rtol=0, atol=1e-5)
 
 
+def test_scaled_and_biased_filter_blocks_agree(hw, monkeypatch):
+    """The filter rounds test score / thr >= 1 on query blocks whose thresholds are all positive (queries staged as
+    q / thr: no extra MMA) and fall back to the bias MMA (score - thr >= 0) otherwise.  Both must return the oracle's
+    rows: a clustered catalogue where some queries only see negative scores, huge / tiny query norms, mixed blocks."""
+    n, d, k = 300000, 128, 50
+    rs = np.random.RandomState(55)
+    centre = rs.standard_normal(d).astype(np.float32)
+    t_np = O.unit_length((centre[None, :] + 0.7 * rs.standard_normal((n, d))).astype(np.float32), axis=1)
+    q_np = O.unit_length(rs.standard_normal((300, d)).astype(np.float32), axis=1)
+    q_np[:40] = -O.unit_length((centre[None, :] + 0.5 * rs.standard_normal((40, d))).astype(np.float32), axis=1)  # all scores < 0
+    q_np[40:60] = O.unit_length((centre[None, :] + 0.5 * rs.standard_normal((20, d))).astype(np.float32), axis=1)
+    q_np[60:70] *= 1e6                                                    # any norm is allowed
+    q_np[70:80] *= 1e-6
+    q_np[299] = 0.0                                                       # zero query: every score is 0
+    t, q = torch.from_numpy(t_np).cuda(), torch.from_numpy(q_np).cuda()
+    ref_idx, ref_sc = O.exact_topk(t_np, q_np, k)
+    answers = []
+    for disable in ("0", "1"):
+        monkeypatch.setenv("HWER_DISABLE", disable)                       # read when the index is created
+        index = hw.ops.TopKIndex(t)
+        for sl in (slice(0, 300), slice(0, 40), slice(40, 300), slice(100, 101)):
+            idx, sc, s64 = index.topk(q[sl].contiguous(), k, want_f64=True)
+            assert O.compare_topk(idx.cpu().numpy(), s64.cpu().numpy(), ref_idx[sl], ref_sc[sl]) == 0, (disable, sl)
+        answers.append(index.topk(q, k, want_f64=True))
+    assert torch.equal(answers[0][0], answers[1][0]) and torch.equal(answers[0][2], answers[1][2])
+
+
 def test_more_ties_than_the_selector_holds_falls_back_to_exhaustive_search(hw):
     """more than 16384 rows inside the bf16 margin of the k-th score (duplicated cold-start embeddings)
     used to raise; the reference's KDTree always answers.  Now the marked queries are answered exhaustively --
