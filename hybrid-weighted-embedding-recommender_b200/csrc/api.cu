@@ -87,7 +87,8 @@ struct hwer_index {
     int env_growth = 0;
     // HWER_DISABLE bit mask for A/B runs (measured in profiles/r02_*_ab.txt): 1 = bias MMA instead of scaled queries,
     // 2 = only the full-capacity final shape; and three alternatives that measured no better and are off by default:
-    // 4 = warp-per-query final, 8 = spill extraction fused into the filter kernel, 16 = warp-per-query dense select
+    // 4 = warp-per-query final, 8 = spill extraction fused into the filter kernel, 16 = warp-per-query dense select;
+    // 32 = no extra CTAs on the SMs left over by slots * query blocks
     int env_disable = 0;
     // optional live profiling of the dominant (filter) kernel with CUDA events on the launching stream
     bool prof = false;
@@ -139,12 +140,14 @@ int ensure_spill(hwer_index* ix, int Bc, int k, int growth) {
     const double per_thread = 1.4 * k * growth * (double)Bc / (double)hwer::filter_tc_spill_buffers(ix->num_sms);
     // ceiling: 128 entries per thread (465 MB), or 512 (1.9 GB) when HBM has room -- top-1000 at batch 4096
     // (config C5) expects ~150 entries per thread and round, and a full buffer means blocking appends
-    size_t free_b = 0, total_b = 0;
-    int ceiling = 128;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > ((size_t)16 << 30)) ceiling = 512;
     int want = 16;
-    while (want < 2.0 * per_thread + 8.0 && want < ceiling) want <<= 1;
+    while (want < 2.0 * per_thread + 8.0 && want < 512) want <<= 1;
     if (want <= ix->spill_cap) return HWER_OK;      // grow-only: a larger buffer serves every smaller request
+    if (want > 128) {                               // (asked only when growing: cudaMemGetInfo costs ~1 ms)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < ((size_t)16 << 30)) want = 128;
+        if (want <= ix->spill_cap) return HWER_OK;
+    }
     HWER_CUDA(cudaDeviceSynchronize());
     if (ix->spill) cudaFree(ix->spill);
     if (ix->spill_cnt) cudaFree(ix->spill_cnt);
@@ -417,6 +420,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics
                 p.spill = ix->spill; p.spill_cnt = ix->spill_cnt; p.spill_cap = ix->spill_cap; p.spill_ctas = ix->num_sms;
                 p.fused_extract = (ix->env_disable & 8) ? 1 : 0;
+                p.no_extra_ctas = (ix->env_disable & 32) ? 1 : 0;
                 HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
                 if (round > 0 && !p.fused_extract) ix->other_launches += 1;     // spill_extract_kernel behind the filter
             } else {
@@ -856,6 +860,23 @@ int hwer_ncf_score(const float* h_dev, int64_t n_rows, int32_t F, int32_t depth,
         return fail(HWER_E_INVALID, "hwer_ncf_score: bad argument (F must be a positive multiple of 4)");
     if (P == 0) return HWER_OK;
     cudaStream_t stream = (cudaStream_t)stream_v;
+    static const int no_tc = getenv("HWER_NCF_FFMA") ? atoi(getenv("HWER_NCF_FFMA")) : 0;     // A/B knob, read once
+    if (hwer::ncf_tc_supported(F, depth) && !no_tc) {
+        // tensor-core path (split-bf16, ncf_tc.cu): serving widths F = 64, 128, 256
+        int dev = 0, sms = 0;
+        HWER_CUDA(cudaGetDevice(&dev));
+        HWER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        long long chunk = hwer::ncf_tc_chunk(sms);
+        const long long p_pad = (P + 127) / 128 * 128;
+        if (chunk > p_pad) chunk = p_pad;
+        void* scratch = nullptr;
+        HWER_CUDA(cudaMallocAsync(&scratch, hwer::ncf_tc_scratch_elems(F, depth, chunk) * 2, stream));
+        cudaError_t e = hwer::launch_ncf_score_tc(h_dev, n_rows, F, depth, params_dev, (const long long*)src_dev,
+                                                  (const long long*)dst_dev, P, out_dev, scratch, chunk, sms, stream);
+        cudaFreeAsync(scratch, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "hwer_ncf_score (tensor-core path)");
+        return HWER_OK;
+    }
     const long long chunk = P < 32768 ? P : 32768;
     float *ws0 = nullptr, *ws1 = nullptr;
     HWER_CUDA(cudaMallocAsync(&ws0, sizeof(float) * (size_t)chunk * 4 * F, stream));

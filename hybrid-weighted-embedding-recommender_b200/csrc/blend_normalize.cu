@@ -30,8 +30,10 @@ __device__ __forceinline__ void store_bf16_row_chunk(__nv_bfloat16* dst, const f
     stg_stream_u2(reinterpret_cast<uint2*>(dst), u);
 }
 
-// VEC = float4 per lane (d4 = d/4 <= 32*VEC).  HAS_C: blend with a content row.
-template <int VEC, bool HAS_C>
+// VEC = float4 per lane (d4 = d/4 <= 32*VEC).  HAS_C: blend with a content row.  A warp works on kRowsPerWarp (2) rows at
+// a time: all their loads are issued before the first reduction, so a lane has 2 * VEC * kRowsPerWarp 128-bit loads
+// in flight (one row per warp left the kernel at 0.85 of copy bandwidth: too few bytes in flight per SM).
+template <int VEC, bool HAS_C, int kRowsPerWarp = (VEC <= 2 ? 2 : 1)>     // wider rows: registers allow one row
 __global__ void __launch_bounds__(kRowThreads)
 blend_normalize_vec_kernel(const float* __restrict__ content, const float* __restrict__ collab, float alpha,
                            const float* __restrict__ alpha_rows, long long n, int d, float* __restrict__ out_f32,
@@ -39,61 +41,70 @@ blend_normalize_vec_kernel(const float* __restrict__ content, const float* __res
     const int lane = lane_id();
     const int d4 = d >> 2;
     const long long warps_total = (long long)gridDim.x * (kRowThreads / 32);
-    for (long long row = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5); row < n;
-         row += warps_total) {
-        float4 g[VEC], c[VEC];
-        const float4* gp = reinterpret_cast<const float4*>(collab + (size_t)row * d);
-        const float4* cp = HAS_C ? reinterpret_cast<const float4*>(content + (size_t)row * d) : nullptr;
-        float sg = 0.f, sc = 0.f;
+    for (long long row0 = ((long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5)) * kRowsPerWarp; row0 < n;
+         row0 += warps_total * kRowsPerWarp) {
+        float4 g[kRowsPerWarp][VEC], c[kRowsPerWarp][VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const int j = lane + 32 * i;
-            g[i] = (j < d4) ? ldg_stream_f4(gp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (HAS_C) c[i] = (j < d4) ? ldg_stream_f4(cp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            sg = fmaf(g[i].x, g[i].x, sg); sg = fmaf(g[i].y, g[i].y, sg);
-            sg = fmaf(g[i].z, g[i].z, sg); sg = fmaf(g[i].w, g[i].w, sg);
-            if (HAS_C) {
-                sc = fmaf(c[i].x, c[i].x, sc); sc = fmaf(c[i].y, c[i].y, sc);
-                sc = fmaf(c[i].z, c[i].z, sc); sc = fmaf(c[i].w, c[i].w, sc);
-            }
-        }
-        const float ng = sqrtf(warp_sum(sg));
-        float sv = 0.f;
-        if (HAS_C) {
-            const float nc = sqrtf(warp_sum(sc));
-            const float a = alpha_rows ? alpha_rows[row] : alpha;
-            // unit() of each source first, as the spec composes them; the two inner normalisations use one
-            // reciprocal per row (an IEEE divide per element made this kernel instruction-bound), the final
-            // one below stays a true division like numpy's
-            const float wc = a * (1.0f / nc), wg = (1.0f - a) * (1.0f / ng);
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const long long row = row0 + r < n ? row0 + r : n - 1;      // a clamped duplicate row is computed, not stored
+            const float4* gp = reinterpret_cast<const float4*>(collab + (size_t)row * d);
+            const float4* cp = HAS_C ? reinterpret_cast<const float4*>(content + (size_t)row * d) : nullptr;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                g[i].x = fmaf(wc, c[i].x, wg * g[i].x);
-                g[i].y = fmaf(wc, c[i].y, wg * g[i].y);
-                g[i].z = fmaf(wc, c[i].z, wg * g[i].z);
-                g[i].w = fmaf(wc, c[i].w, wg * g[i].w);
-                sv = fmaf(g[i].x, g[i].x, sv); sv = fmaf(g[i].y, g[i].y, sv);
-                sv = fmaf(g[i].z, g[i].z, sv); sv = fmaf(g[i].w, g[i].w, sv);
+                const int j = lane + 32 * i;
+                g[r][i] = (j < d4) ? ldg_stream_f4(gp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_C) c[r][i] = (j < d4) ? ldg_stream_f4(cp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        const float nv = HAS_C ? sqrtf(warp_sum(sv)) : ng;
-        float4* op = reinterpret_cast<float4*>(out_f32 + (size_t)row * d);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const int j = lane + 32 * i;
-            float4 o;
-            o.x = g[i].x / nv; o.y = g[i].y / nv; o.z = g[i].z / nv; o.w = g[i].w / nv;
-            if (j < d4) {
-                stg_stream_f4(op + j, o);
-                if (out_bf16) store_bf16_row_chunk(out_bf16 + (size_t)row * d_pad + 4 * j, o);
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const long long row = row0 + r;
+            if (row >= n) break;
+            float sg = 0.f, sc = 0.f;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                sg = fmaf(g[r][i].x, g[r][i].x, sg); sg = fmaf(g[r][i].y, g[r][i].y, sg);
+                sg = fmaf(g[r][i].z, g[r][i].z, sg); sg = fmaf(g[r][i].w, g[r][i].w, sg);
+                if (HAS_C) {
+                    sc = fmaf(c[r][i].x, c[r][i].x, sc); sc = fmaf(c[r][i].y, c[r][i].y, sc);
+                    sc = fmaf(c[r][i].z, c[r][i].z, sc); sc = fmaf(c[r][i].w, c[r][i].w, sc);
+                }
             }
-        }
-        if (out_bf16) {   // zero the padding columns [d, d_pad)
-            for (int col = d + 4 * lane; col < d_pad; col += 128)
-                stg_stream_u2(reinterpret_cast<uint2*>(out_bf16 + (size_t)row * d_pad + col), make_uint2(0u, 0u));
+            const float ng = sqrtf(warp_sum(sg));
+            float sv = 0.f;
+            if (HAS_C) {
+                const float nc = sqrtf(warp_sum(sc));
+                const float a = alpha_rows ? alpha_rows[row] : alpha;
+                // unit() of each source first, as the spec composes them; the two inner normalisations use one
+                // reciprocal per row (an IEEE divide per element made this kernel instruction-bound), the final
+                // one below stays a true division like numpy's
+                const float wc = a * (1.0f / nc), wg = (1.0f - a) * (1.0f / ng);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    g[r][i].x = fmaf(wc, c[r][i].x, wg * g[r][i].x);
+                    g[r][i].y = fmaf(wc, c[r][i].y, wg * g[r][i].y);
+                    g[r][i].z = fmaf(wc, c[r][i].z, wg * g[r][i].z);
+                    g[r][i].w = fmaf(wc, c[r][i].w, wg * g[r][i].w);
+                    sv = fmaf(g[r][i].x, g[r][i].x, sv); sv = fmaf(g[r][i].y, g[r][i].y, sv);
+                    sv = fmaf(g[r][i].z, g[r][i].z, sv); sv = fmaf(g[r][i].w, g[r][i].w, sv);
+                }
+            }
+            const float nv = HAS_C ? sqrtf(warp_sum(sv)) : ng;
+            float4* op = reinterpret_cast<float4*>(out_f32 + (size_t)row * d);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int j = lane + 32 * i;
+                float4 o;
+                o.x = g[r][i].x / nv; o.y = g[r][i].y / nv; o.z = g[r][i].z / nv; o.w = g[r][i].w / nv;
+                if (j < d4) {
+                    stg_stream_f4(op + j, o);
+                    if (out_bf16) store_bf16_row_chunk(out_bf16 + (size_t)row * d_pad + 4 * j, o);
+                }
+            }
+            if (out_bf16) {   // zero the padding columns [d, d_pad)
+                for (int col = d + 4 * lane; col < d_pad; col += 128)
+                    stg_stream_u2(reinterpret_cast<uint2*>(out_bf16 + (size_t)row * d_pad + col), make_uint2(0u, 0u));
+            }
         }
     }
 }
@@ -180,20 +191,35 @@ norm_stats_kernel(const float* __restrict__ v, long long n, int d, float eps, do
     }
 }
 
-// Fixed-order final reduction: out5 = {violations, mean|norm-1|, positive, negative, max norm}
-__global__ void norm_stats_reduce_kernel(const double* __restrict__ partial, int nblocks, long long n,
-                                         double* __restrict__ out5) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Fixed-order final reduction: out5 = {violations, mean|norm-1|, positive, negative, max norm}.  One CTA: thread t
+// sums partials t, t + 256, ... in ascending order, then a fixed binary tree over the 256 threads -- the same
+// association for a given grid size on every run (r1 walked the ~2400 partials with ONE thread: 53 us).
+__global__ void __launch_bounds__(256)
+norm_stats_reduce_kernel(const double* __restrict__ partial, int nblocks, long long n, double* __restrict__ out5) {
+    __shared__ double sh[4][256];
     double a = 0, b = 0, c = 0, m = 0;
-    for (int i = 0; i < nblocks; ++i) {
+    for (int i = threadIdx.x; i < nblocks; i += 256) {
         a += partial[4 * i]; b += partial[4 * i + 1]; c += partial[4 * i + 2];
         if (!(partial[4 * i + 3] <= m)) m = partial[4 * i + 3];
     }
-    out5[0] = a + b;
-    out5[1] = n > 0 ? c / (double)n : 0.0;
-    out5[2] = a;
-    out5[3] = b;
-    out5[4] = m;
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b; sh[2][threadIdx.x] = c; sh[3][threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + s];
+            if (!(sh[3][threadIdx.x + s] <= sh[3][threadIdx.x])) sh[3][threadIdx.x] = sh[3][threadIdx.x + s];   // NaN wins
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out5[0] = sh[0][0] + sh[1][0];
+        out5[1] = n > 0 ? sh[2][0] / (double)n : 0.0;
+        out5[2] = sh[0][0];
+        out5[3] = sh[1][0];
+        out5[4] = sh[3][0];
+    }
 }
 
 // fp32 table -> zero-padded bf16 shadow (round-to-nearest-even), no normalisation.
@@ -265,7 +291,7 @@ cudaError_t launch_norm_stats(const float* v, long long n, int d, float eps, dou
     cudaError_t e = cudaMallocAsync(&partial, sizeof(double) * 4 * grid, stream);
     if (e != cudaSuccess) return e;
     norm_stats_kernel<<<grid, kRowThreads, 0, stream>>>(v, n, d, eps, partial);
-    norm_stats_reduce_kernel<<<1, 32, 0, stream>>>(partial, grid, n, out5);
+    norm_stats_reduce_kernel<<<1, 256, 0, stream>>>(partial, grid, n, out5);
     e = cudaGetLastError();
     cudaFreeAsync(partial, stream);
     return e;

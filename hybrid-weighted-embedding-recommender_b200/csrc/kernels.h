@@ -31,6 +31,9 @@ struct FilterParams {
     int nqb;                  // number of query blocks = ceil(B / nq)
     int slots;                // CTAs cooperating on one query block (split of the item tiles)
     int qb_step;              // query blocks advanced per outer iteration (= gridDim.x / slots)
+    int extra;                // CTAs beyond slots * nqb that share the tail tiles [tile_split, tile_end) (score_filter.cu)
+    int tile_split;
+    int no_extra_ctas;        // A/B knob
     const float* thr;         // [B] current per-query admission threshold
     const float* floor;       // [B] finite lower bound of any score of the query (stands in for thr = -inf)
     const float* qmax;        // [B] largest |component| of the query (overflow guard of the scaled filter)
@@ -192,5 +195,13 @@ long long ncf_param_count(int F, int depth);
 cudaError_t launch_ncf_score(const float* h, long long n_rows, int F, int depth, const float* params,
                              const long long* src, const long long* dst, long long P, float* out, float* ws0,
                              float* ws1, long long chunk, cudaStream_t stream);
+
+// tcgen05 path of the NCF re-rank (ncf_tc.cu): split-bf16 operands, F % 64 == 0, F <= 256.
+bool ncf_tc_supported(int F, int depth);
+long long ncf_tc_chunk(int num_sms);
+size_t ncf_tc_scratch_elems(int F, int depth, long long chunk);      // bf16 elements
+cudaError_t launch_ncf_score_tc(const float* h, long long n_rows, int F, int depth, const float* params,
+                                const long long* src, const long long* dst, long long P, float* out, void* scratch,
+                                long long chunk, int num_sms, cudaStream_t stream);
 
 }  // namespace hwer

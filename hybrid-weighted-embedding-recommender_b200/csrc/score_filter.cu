@@ -173,6 +173,28 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
     }
 }
 
+// Which query blocks and which tiles a CTA of the filter grid walks.  Regular CTAs: `slots` CTAs share one query
+// block and stride over the tiles [tile_begin, tile_split).  When the SM count is not a multiple of the number of
+// query blocks (148 SMs, 16 blocks of a 4096-query batch: 9 slots = 144 CTAs), the `extra` left-over CTAs take the
+// tail [tile_split, tile_end) instead, each for every extra-th query block in turn -- sized on the host so that
+// every CTA of the grid scores the same number of tiles.
+struct CtaWork {
+    int qb0, qb_step;          // query blocks qb0, qb0 + qb_step, ... < nqb
+    int t_first, t_stride, t_end;
+};
+__device__ __forceinline__ CtaWork cta_work(const FilterParams& p, int bid) {
+    CtaWork w;
+    const int regular = p.slots * (p.nqb < p.qb_step ? p.nqb : p.qb_step);
+    if (p.extra > 0 && bid >= regular) {
+        w.qb0 = bid - regular; w.qb_step = p.extra;
+        w.t_first = p.tile_split; w.t_stride = 1; w.t_end = p.tile_end;
+    } else {
+        w.qb0 = bid / p.slots; w.qb_step = p.qb_step;
+        w.t_first = p.tile_begin + bid % p.slots; w.t_stride = p.slots; w.t_end = p.extra > 0 ? p.tile_split : p.tile_end;
+    }
+    return w;
+}
+
 // The per-hit work the filter kernel's epilogue does not do.  Block b owns the 512 spill buffers of filter CTA b,
 // one thread per buffer.  All of a filter CTA's hits belong to the (usually one) query block it scored, so the
 // block first COUNTS its hits per query in shared memory, reserves one contiguous range per query in the global
@@ -199,7 +221,8 @@ spill_extract_kernel(const __grid_constant__ FilterParams p) {
     const uint4* e0 = p.spill + buf * (size_t)p.spill_cap * 3;
     const int nq = p.nq;
     unsigned int cursor = (unsigned int)(tid % kExtractSub);         // this thread's entries: cursor, cursor + Sub, ...
-    for (int qb = (int)blockIdx.x / p.slots; qb < p.nqb; qb += p.qb_step) {     // the filter CTA's query blocks
+    const CtaWork work = cta_work(p, (int)blockIdx.x);
+    for (int qb = work.qb0; qb < p.nqb; qb += work.qb_step) {                   // the filter CTA's query blocks
         const int q_base = qb * nq;
         bool ok = true;                                                         // the filter CTA's own vote, recomputed
         for (int i = tid; i < nq; i += kExtractThreads) {
@@ -379,16 +402,17 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int slot = blockIdx.x % p.slots;
-    const int qb0 = blockIdx.x / p.slots;
+    const CtaWork work = cta_work(p, (int)blockIdx.x);
+    const int qb0 = work.qb0;
     const uint32_t idesc = umma_idesc_bf16_f32(kTileItems, (uint32_t)nq);
     const uint64_t policy = p.stream_once ? l2_policy_evict_first() : l2_policy_evict_last();
 
     // Tiles this CTA walks per query block, and the visiting order (32-bit: tile counts fit easily).
-    const int t_first = p.tile_begin + slot;
-    const int my_tiles = t_first < p.tile_end ? (p.tile_end - t_first + p.slots - 1) / p.slots : 0;
+    const int t_first = work.t_first;
+    const int my_tiles = t_first < work.t_end ? (work.t_end - t_first + work.t_stride - 1) / work.t_stride : 0;
     const uint32_t phys0 = (uint32_t)(((long long)t_first * p.tile_mul) % p.tile_mod);
-    const uint32_t tile_step = (uint32_t)p.tile_step, tile_mod = (uint32_t)p.tile_mod;
+    const uint32_t tile_mod = (uint32_t)p.tile_mod;
+    const uint32_t tile_step = work.t_stride == 1 ? (uint32_t)(p.tile_mul % p.tile_mod) : (uint32_t)p.tile_step;
     // Ring positions persist across query blocks; every role keeps private copies (so they can live in uniform
     // registers where the role is warp-converged) re-derived from this count at the top of each block.
     uint32_t tiles_done = 0;
@@ -399,7 +423,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     if (MODE == kModeFilter && warp >= 2)
         sp.mine = p.spill + ((size_t)blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64)) * (size_t)p.spill_cap * 3;
 
-    for (int qb = qb0; qb < p.nqb; qb += p.qb_step) {
+    for (int qb = qb0; qb < p.nqb; qb += work.qb_step) {
         const int q_base = qb * nq;
         // ---- thresholds of the block, and how it will be filtered (scaled queries or the bias MMA) ----
         bool scaled = false;
@@ -544,7 +568,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 phys += tile_step;
                 if (phys >= tile_mod) phys -= tile_mod;
                 const bool row_ok = row < n_items;
-                const uint32_t dense_pos = (uint32_t)(t_first - p.tile_begin + it * p.slots) * (uint32_t)kTileItems + lane_row;
+                const uint32_t dense_pos = (uint32_t)(t_first - p.tile_begin + it * work.t_stride) * (uint32_t)kTileItems + lane_row;
                 if (scaled) {
                     epilogue_chunk<MODE, true>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
                     if (two) epilogue_chunk<MODE, true>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
@@ -704,11 +728,26 @@ cudaError_t launch_filter_tc(const CUtensorMap& tmap, FilterParams p, int num_sm
     p.tmem_cols = pow2;
     const int ntiles = p.tile_end - p.tile_begin;
     int grid;
+    p.extra = 0;
+    p.tile_split = p.tile_end;
     if (p.nqb <= num_sms) {
         p.slots = num_sms / p.nqb;
         if (p.slots > ntiles) p.slots = ntiles;
         p.qb_step = p.nqb;
         grid = p.slots * p.nqb;
+        // left-over SMs (148 - 9 * 16 = 4 at B = 4096): give them the tail of the round, a quarter of the query
+        // blocks each, sized so that all CTAs score the same number of tiles: (split - begin) / slots ==
+        // ceil(nqb / extra) * (end - split)
+        const int extra = num_sms - grid;
+        if (extra > 0 && p.nqb > 1 && !p.no_extra_ctas && p.slots == num_sms / p.nqb) {
+            const int per_extra = (p.nqb + extra - 1) / extra;                      // query blocks per extra CTA
+            const int tail = (int)((long long)ntiles / ((long long)p.slots * per_extra + 1));
+            if (tail >= 8) {
+                p.extra = extra;
+                p.tile_split = p.tile_end - tail;
+                grid += extra;
+            }
+        }
     } else {
         p.slots = 1;
         p.qb_step = num_sms;

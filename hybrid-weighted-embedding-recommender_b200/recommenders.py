@@ -82,15 +82,31 @@ class GcnNCF(RecommendationBase):
         res = super().predict(node_pairs)
         return list(res) if self.ncf_enabled else res      # the reference returns a list here (gcn_ncf.py:360-361)
 
+    def _pca_reduce(self, vectors, dev):
+        """PCA(n_components=n_dims).fit_transform of hwer/gcn_ncf.py:449-452 on the device: centre, covariance
+        (one cuBLAS GEMM), symmetric eigendecomposition (cuSOLVER), projection on the n_dims leading axes, with
+        sklearn's sign rule (each axis' largest-magnitude loading is positive).  An offline step of fit(), run once
+        per table -- library calls, not hot-path kernels.  The reference's call leaves the solver to sklearn's 'auto'
+        (randomised and unseeded for large tables), so its own output is only defined up to that solver's error; this
+        is the exact ('full') decomposition in float64, rounded to fp32 like the reference's result."""
+        x = vectors if isinstance(vectors, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(vectors))
+        x = x.to(dev, torch.float64)
+        x = x - x.mean(dim=0, keepdim=True)
+        evals, evecs = torch.linalg.eigh(x.t() @ x)                   # ascending eigenvalues
+        axes = evecs[:, -self.n_dims:].flip(1)                        # [D, n_dims], leading axis first
+        lead = axes.abs().argmax(dim=0)
+        axes = axes * torch.sign(axes[lead, torch.arange(axes.shape[1], device=dev)])[None, :]
+        return (x @ axes).float().contiguous()
+
     def prepare_for_knn(self, content_vectors, collaborative_vectors, alpha=None):
         """unit(alpha * unit(content) + (1 - alpha) * unit(collaborative)) on the device; numpy in -> numpy out."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        as_tensor = isinstance(collaborative_vectors, torch.Tensor)      # tensor in -> tensor out, numpy in -> numpy out
         if collaborative_vectors.shape[1] > self.n_dims:
-            # the reference reduces with sklearn PCA here (gcn_ncf.py:449-452): an offline step, not served
-            raise ValueError("collaborative table is wider than n_dims; reduce it offline (PCA) first")
+            collaborative_vectors = self._pca_reduce(collaborative_vectors, dev)        # gcn_ncf.py:449-452
         elif collaborative_vectors.shape[1] < self.n_dims:
             raise ValueError()
         alpha = self.alpha if alpha is None else alpha
-        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
         g = _as_device_table(collaborative_vectors, dev)
         use_content = content_vectors is not None and not (isinstance(alpha, float) and alpha == 0.0)
         c = None
@@ -102,7 +118,7 @@ class GcnNCF(RecommendationBase):
             alpha = torch.from_numpy(alpha.astype(np.float32)).to(dev)
         table, self.shadow = ops.blend_normalize(c, g, alpha if use_content else 0.0)
         self._device_table = table
-        if isinstance(collaborative_vectors, torch.Tensor):
+        if as_tensor:
             return table
         return table.cpu().numpy()
 

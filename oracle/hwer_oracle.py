@@ -58,6 +58,23 @@ def blend_normalize(content, collab, alpha):
     return unit_length(a * c + (1 - a) * g, axis=1)
 
 
+def prepare_for_knn(collaborative_vectors, n_dims):
+    """hwer/gcn_ncf.py:447-456 (content_vectors is ignored there): PCA to n_dims when the table is wider -- sklearn's
+    PCA, a third-party dependency outside /root/reference, restated as the exact decomposition: centre, SVD, project
+    on the leading right singular vectors, each flipped so that its largest-magnitude loading is positive (sklearn's
+    svd_flip rule) -- then unit_length.  Equal up to solver error to whatever solver sklearn's 'auto' picks."""
+    x = np.asarray(collaborative_vectors)
+    if x.shape[1] > n_dims:
+        xc = x.astype(np.float64) - x.astype(np.float64).mean(axis=0)
+        _, _, vt = np.linalg.svd(xc, full_matrices=False)
+        vt = vt[:n_dims]
+        vt = vt * np.sign(vt[np.arange(n_dims), np.abs(vt).argmax(axis=1)])[:, None]
+        x = (xc @ vt.T).astype(np.float32)
+    elif x.shape[1] < n_dims:
+        raise ValueError()
+    return unit_length(x, axis=1)
+
+
 def reciprocal_rank(y_true, y_pred):
     """hwer/utils.py:71-78."""
     y_true = set(y_true)

@@ -763,6 +763,22 @@ def test_ncf_eval_matches_reference(hw, golden_eval, golden_r2):
                                rtol=0, atol=1e-12)
 
 
+def test_prepare_for_knn_pca_branch_matches_reference(hw, golden_r2):
+    """GcnNCF.prepare_for_knn reduces a table wider than n_dims with PCA (hwer/gcn_ncf.py:449-452) before the unit
+    normalisation; the reference's own output on the same 400 x 96 table."""
+    rs = np.random.RandomState(700)
+    wide = (rs.standard_normal((400, 96)) * np.linspace(3.0, 0.2, 96)[None, :]).astype(np.float32)
+    m = hw.GcnNCF(None, {"user", "item"}, n_dims=32)
+    got = m.prepare_for_knn(None, wide)
+    assert isinstance(got, np.ndarray) and got.shape == (400, 32)
+    # sklearn decomposes the fp32 table in fp32: axes with close eigenvalues rotate by ~1e-4 against the float64
+    # decomposition, while the Gram matrix -- all that retrieval sees -- agrees to 1e-5
+    np.testing.assert_allclose(got, golden_r2["pca_table"], rtol=0, atol=3e-4)
+    np.testing.assert_allclose(got @ got.T, golden_r2["pca_table"] @ golden_r2["pca_table"].T, rtol=0, atol=2e-5)
+    with pytest.raises(ValueError):
+        m.prepare_for_knn(None, wide[:, :16])
+
+
 def test_get_topk_hook_is_honoured(hw, golden_eval):
     """extraction_efficiency(model, train, val, get_topk, node_type) calls the hook it is given
     (hwer/validation.py:100,111) and evaluates what it returns."""

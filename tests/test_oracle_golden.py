@@ -315,3 +315,16 @@ def test_ncf_eval_matches_reference(golden_eval, golden_r2):
     random.seed(int(golden_r2["ncf_eval_seed"][0]))
     hr, nd, _ = O.ncf_eval(m, train, val, all_items, random)
     np.testing.assert_allclose([hr, nd], golden_r2["ncf_eval"], rtol=0, atol=1e-12)
+
+
+def test_prepare_for_knn_pca_branch_matches_reference(golden_r2):
+    rs = np.random.RandomState(700)
+    wide = (rs.standard_normal((400, 96)) * np.linspace(3.0, 0.2, 96)[None, :]).astype(np.float32)
+    got = O.prepare_for_knn(wide, 32)
+    assert got.shape == (400, 32)
+    # sklearn decomposes the fp32 table in fp32: axes with close eigenvalues rotate by ~1e-4 against the float64
+    # decomposition, while the Gram matrix -- all that retrieval sees -- agrees to 1e-5
+    np.testing.assert_allclose(got, golden_r2["pca_table"], rtol=0, atol=3e-4)
+    np.testing.assert_allclose(got @ got.T, golden_r2["pca_table"] @ golden_r2["pca_table"].T, rtol=0, atol=2e-5)
+    with pytest.raises(ValueError):
+        O.prepare_for_knn(wide[:, :16], 32)
