@@ -454,14 +454,19 @@ def run_b200(a):
             torch.cuda.synchronize()
     else:
         q_host = queries_for(a.batch).cpu().pin_memory()
-        sc_host = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
-        e2e_api = "ShardedTopK.topk(<pinned host queries>, k=%d)" % a.k if world > 1 else "TopKIndex.topk"
-        h2d, d2h = a.batch * a.dim * 4, a.batch * a.k * 12
+        # N > 1: every rank uploads the (replicated) query batch and copies out the rows of the queries it merged
+        # (ShardedTopK.topk(owned=True)): each query's answer reaches exactly one host buffer, 1/N of the result per rank
+        lo, hi = shard.owner_range(a.batch) if world > 1 else (0, a.batch)
+        idx_host = torch.empty((hi - lo, a.k), dtype=torch.int64).pin_memory()
+        sc_host = torch.empty((hi - lo, a.k), dtype=torch.float32).pin_memory()
+        e2e_api = ("ShardedTopK.topk(<pinned host queries>, k=%d, owned=True): rank r copies out the %d queries it merged"
+                   % (a.k, hi - lo)) if world > 1 else "TopKIndex.topk"
+        h2d, d2h = a.batch * a.dim * 4, (hi - lo) * a.k * 12
 
         def step_e2e():
             q = q_host.to(dev, non_blocking=True)
             if world > 1:
-                idx, sc = shard.topk(q, a.k, a.mode)
+                idx, sc = shard.topk(q, a.k, a.mode, owned=True)
             else:
                 idx, sc = index.topk(q, a.k, a.mode, idx_offset=begin)
             idx_host.copy_(idx, non_blocking=True)

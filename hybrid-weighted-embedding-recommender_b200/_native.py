@@ -17,7 +17,7 @@ HWER_E_OVERFLOW = -5
 HWER_E_NOMEM = -6
 HWER_E_PEER = -7
 IPC_HANDLE_BYTES = 64
-PHASE_SEARCH, PHASE_MERGE, PHASE_COLLECT, PHASE_ALL = 1, 2, 4, 7
+PHASE_SEARCH, PHASE_MERGE, PHASE_COLLECT, PHASE_ALL, PHASE_OWNED = 1, 2, 4, 7, 8
 MODE_EXACT = 0
 MODE_BF16 = 1
 SCORE_PAIR, SCORE_DIST, SCORE_GIVEN, SCORE_EUCLID = 0, 1, 2, 3

@@ -195,8 +195,11 @@ int make_schedule(const hwer_index* ix, int B, int k, unsigned int cap_user, int
     const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
     long long first_rows = (B > 512 || (B > 16 && B <= 128)) ? 4096 : 8192;
     int g = B <= 16 ? 32 : (B <= 128 ? 16 : (B <= 512 ? 4 : 2));
-    if (first_rows < 2LL * k) first_rows = 2LL * k;
-    if (ix->env_first_rows >= 2LL * k && ix->env_first_rows <= max_cap) first_rows = ix->env_first_rows;   // tuning knob
+    // round 0 must leave every list with the k candidates its select needs (shards that share thresholds publish
+    // their ceil(k / G)-th best, so they need that many)
+    const long long k_need = world_share > 1 ? (k + world_share - 1) / world_share : k;
+    if (first_rows < 2LL * k_need) first_rows = 2LL * k_need;
+    if (ix->env_first_rows >= 2LL * k_need && ix->env_first_rows <= max_cap) first_rows = ix->env_first_rows;   // tuning knob
     s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
     first_rows = s->first_tiles * hwer::kTileItems;
     while (g > 1 && 3LL * k * g > max_cap) g >>= 1;
@@ -386,13 +389,12 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
     for (long long q0 = 0; q0 < B; q0 += (long long)chunk, ++chunk_idx) {
         const int Bc = (int)(((long long)B - q0) < (long long)chunk ? ((long long)B - q0) : (long long)chunk);
         const float* Q = queries_dev + (size_t)q0 * ix->d;
-        HWER_CUDA(cudaMemsetAsync(ix->cnt, 0, sizeof(unsigned int) * Bc, stream));
-        HWER_CUDA(cudaMemsetAsync(ix->ovf, 0, sizeof(unsigned int) * Bc, stream));
-        HWER_CUDA(hwer::launch_fill_f32(ix->thr, Bc, -INFINITY, stream));
         // the CUDA-core path scores in fp32: its (tiny) margin keeps even bf16-less indexes exact
         const float* margin = (exact || !ix->use_tc) ? ix->margin : nullptr;
-        HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->max_norm, ix->margin, ix->floor, ix->qmax, stream));
-        ix->other_launches += 3;   // fill + margin/floor + final
+        // one launch: margin / floor / overflow guard per query + reset of its count, overflow mark and threshold
+        HWER_CUDA(hwer::launch_query_margin(Q, Bc, ix->d, margin_factor, ix->max_norm, ix->margin, ix->floor, ix->qmax,
+                                            ix->cnt, ix->ovf, ix->thr, stream));
+        ix->other_launches += 2;   // set-up + final
         long long seen = 0;
         int round = 0;
         while (seen < T_sched) {
@@ -605,11 +607,12 @@ int hwer_topk_sharded(hwer_index_t* ix, hwer_exchange_t* x, const float* queries
     if (phases & HWER_PHASE_SEARCH) ++x->epoch;     // every rank calls in lockstep, so they agree on it
     const unsigned int epoch = x->epoch;
     x->v.q_per_owner = (B + x->v.world - 1) / x->v.world;
+    const int owned = (phases & HWER_PHASE_OWNED) ? 1 : 0;
     if (!(phases & HWER_PHASE_SEARCH)) {
-        if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));
+        if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, owned, stream));
         if (phases & HWER_PHASE_COLLECT)
             HWER_CUDA(hwer::launch_exchange_collect(x->v, B, k, epoch, (long long*)out_idx_dev, out_score_dev,
-                                                    out_score64_dev, ix->needed_dev, stream));
+                                                    out_score64_dev, ix->needed_dev, owned, stream));
         return HWER_OK;
     }
     hwer::PeerDst pd;
@@ -622,10 +625,10 @@ int hwer_topk_sharded(hwer_index_t* ix, hwer_exchange_t* x, const float* queries
     if (rc) return rc;
     const bool timed_x = prof_begin(ix, stream, kStageExchange);
     HWER_CUDA(hwer::launch_exchange_signal(x->v, 0, epoch, ix->needed_dev, stream));
-    if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, stream));
+    if (phases & HWER_PHASE_MERGE) HWER_CUDA(hwer::launch_exchange_merge(x->v, B, k, epoch, owned, stream));
     if (phases & HWER_PHASE_COLLECT)
         HWER_CUDA(hwer::launch_exchange_collect(x->v, B, k, epoch, (long long*)out_idx_dev, out_score_dev,
-                                                out_score64_dev, ix->needed_dev, stream));
+                                                out_score64_dev, ix->needed_dev, owned, stream));
     prof_end(ix, stream, timed_x);
     ix->other_launches += 3;
     return HWER_OK;

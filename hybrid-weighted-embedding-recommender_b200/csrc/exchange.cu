@@ -70,7 +70,7 @@ __device__ __forceinline__ int next_pow2_i(int x) {
 }
 
 __global__ void __launch_bounds__(kMergeThreads)
-exchange_merge_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsigned int epoch) {
+exchange_merge_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsigned int epoch, int owned) {
     extern __shared__ unsigned long long sm[];
     __shared__ int ok_s;
     unsigned int* myflags = v.flags[v.rank];
@@ -114,9 +114,11 @@ exchange_merge_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsi
                 __syncthreads();
             }
         }
-        // deliver the k winners of this query to every rank's result area
-        for (int i = threadIdx.x; i < K * v.world; i += blockDim.x) {
-            const int r = i / K, j = i - r * K;
+        // deliver the k winners of this query to every rank's result area (owned: this rank keeps its queries'
+        // results to itself -- HWER_PHASE_OWNED -- and nothing crosses NVLink a second time)
+        const int r_first = owned ? v.rank : 0, r_count = owned ? 1 : v.world;
+        for (int i = threadIdx.x; i < K * r_count; i += blockDim.x) {
+            const int r = r_first + i / K, j = i - (i / K) * K;
             const bool ok = id[j] != 0x7fffffffffffffffll;
             const double s = ok ? ordered_to_f64(sk[j]) : -INFINITY;
             const size_t o = (size_t)qg * K + j;
@@ -140,7 +142,7 @@ exchange_merge_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsi
 __global__ void __launch_bounds__(256)
 exchange_collect_kernel(const __grid_constant__ ExchangeView v, int B, int K, unsigned int epoch,
                         long long* __restrict__ out_idx, float* __restrict__ out_score,
-                        double* __restrict__ out_score64, unsigned int* __restrict__ status2) {
+                        double* __restrict__ out_score64, unsigned int* __restrict__ status2, int owned) {
     unsigned int* myflags = v.flags[v.rank];
     if ((int)threadIdx.x < v.world) wait_epoch(myflags + kMaxPeers + threadIdx.x, epoch, myflags + 17);
     __syncthreads();
@@ -149,10 +151,15 @@ exchange_collect_kernel(const __grid_constant__ ExchangeView v, int B, int K, un
         if (wait_epoch(myflags + threadIdx.x, epoch, myflags + 17)) atomicMax(status2, __ldcv(myflags + 40 + threadIdx.x));
         if (__ldcv(myflags + 17)) atomicMax(status2 + 1, 1u);
     }
-    const size_t n = (size_t)B * K;
-    const long long* si = v.out_idx[v.rank];
-    const float* ss = v.out_score[v.rank];
-    const double* sd = v.out_score64[v.rank];
+    // owned: only the rows this rank merged, [rank * q_per_owner, ...), packed at the front of out_*.  The wait for
+    // every owner's flag above stays: it is what keeps a fast rank from overwriting exchange buffers an owner still reads
+    long long own = (long long)B - (long long)v.rank * v.q_per_owner;
+    own = own > v.q_per_owner ? v.q_per_owner : (own < 0 ? 0 : own);
+    const size_t n = owned ? (size_t)own * K : (size_t)B * K;
+    const size_t o0 = owned ? (size_t)v.rank * v.q_per_owner * K : 0;
+    const long long* si = v.out_idx[v.rank] + o0;
+    const float* ss = v.out_score[v.rank] + o0;
+    const double* sd = v.out_score64[v.rank] + o0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         out_idx[i] = __ldcv(si + i);          // written by peers: never from a stale cache line
         out_score[i] = __ldcv(ss + i);
@@ -180,7 +187,8 @@ cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned in
     return cudaGetLastError();
 }
 
-cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, cudaStream_t stream) {
+cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, int owned,
+                                  cudaStream_t stream) {
     long long own = (long long)B - (long long)v.rank * v.q_per_owner;
     if (own > v.q_per_owner) own = v.q_per_owner;
     if (own <= 0) return launch_exchange_signal(v, 1, epoch, nullptr, stream);      // nothing to merge: just report in
@@ -192,17 +200,18 @@ cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned 
         cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    exchange_merge_kernel<<<(unsigned)own, kMergeThreads, smem, stream>>>(v, B, K, epoch);
+    exchange_merge_kernel<<<(unsigned)own, kMergeThreads, smem, stream>>>(v, B, K, epoch, owned);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exchange_collect(const ExchangeView& v, int B, int K, unsigned int epoch, long long* out_idx,
-                                    float* out_score, double* out_score64, unsigned int* status2, cudaStream_t stream) {
-    const size_t n = (size_t)B * K;
+                                    float* out_score, double* out_score64, unsigned int* status2, int owned,
+                                    cudaStream_t stream) {
+    const size_t n = owned ? (size_t)v.q_per_owner * K : (size_t)B * K;
     int grid = (int)((n + 256 * 8 - 1) / (256 * 8));
     if (grid < 1) grid = 1;
     if (grid > 296) grid = 296;
-    exchange_collect_kernel<<<grid, 256, 0, stream>>>(v, B, K, epoch, out_idx, out_score, out_score64, status2);
+    exchange_collect_kernel<<<grid, 256, 0, stream>>>(v, B, K, epoch, out_idx, out_score, out_score64, status2, owned);
     return cudaGetLastError();
 }
 

@@ -73,7 +73,8 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
                                long long row_begin, long long row_end, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float max_norm, float* margin,
-                                float* floor, float* qmax, cudaStream_t stream);
+                                float* floor, float* qmax, unsigned int* cnt, unsigned int* ovf, float* thr,
+                                cudaStream_t stream);
 cudaError_t launch_fill_f32(float* p, long long n, float v, cudaStream_t stream);
 
 // Cross-GPU threshold sharing for a row-sharded catalogue (DESIGN.md "Multi-GPU"): with G shards, the min over
@@ -140,10 +141,11 @@ cudaError_t exchange_preload();      // loads the exchange kernels now (see exch
 // `needed` (phase 0, may be NULL): this rank's candidate-capacity demand, delivered to every peer with the flag
 cudaError_t launch_exchange_signal(const ExchangeView& v, int phase, unsigned int epoch, const unsigned int* needed,
                                    cudaStream_t stream);
-cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, cudaStream_t stream);
-// status2 (may be NULL): [0] is raised (atomicMax) to the largest capacity demand of any rank, [1] set on a peer timeout
+cudaError_t launch_exchange_merge(const ExchangeView& v, int B, int K, unsigned int epoch, int owned,
+                                  cudaStream_t stream);
 cudaError_t launch_exchange_collect(const ExchangeView& v, int B, int K, unsigned int epoch, long long* out_idx,
-                                    float* out_score, double* out_score64, unsigned int* status2, cudaStream_t stream);
+                                    float* out_score, double* out_score64, unsigned int* status2, int owned,
+                                    cudaStream_t stream);
 
 cudaError_t launch_merge(const double* scores, const long long* idx, int G, int B, int K, long long* out_idx,
                          float* out_score, double* out_score64, cudaStream_t stream);

@@ -154,6 +154,24 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
         any = (int)((grp[0] & grp[1]) & (grp[2] & grp[3])) >= 0;
     }
     if (any && row_ok) {                           // this lane's row has an admissible score: rare
+        if (sp.n + 4u <= (uint32_t)p.spill_cap) {
+            // room for all four groups of the chunk (the normal case): no branch per group -- predicated stores and a
+            // running entry pointer.  With two accumulator stages the slowest epilogue warp of a tile paces the tensor
+            // pipe, so the LATENCY of this path (it was four BSSY / branch / BSYNC regions deep) is what a hit costs.
+            uint4* e = sp.mine + (size_t)sp.n * 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const bool hit = scaled ? mx[g] >= 1.0f : (int)grp[g] >= 0;
+                if (hit) {
+                    e[0] = make_uint4(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3]);
+                    e[1] = make_uint4(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]);
+                    e[2] = make_uint4(row, (uint32_t)(q_base + c0 + 8 * g), 0u, 0u);
+                }
+                e += hit ? 3 : 0;
+                sp.n += hit ? 1u : 0u;
+            }
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (scaled ? mx[g] >= 1.0f : (int)grp[g] >= 0) {
@@ -343,6 +361,8 @@ __device__ __forceinline__ void extract_own_spill(const FilterParams& p, const u
 }
 
 template <int MODE, int KB>
+// 18 warps = 5 on one of the SM's four sub-partitions, each with a 16 K-entry register file: 96 registers per thread
+// is the ceiling (16384 / (5 * 32) = 102, allocated in eights), which is why the tile loop spills a little
 __global__ void __launch_bounds__(kThreadsTc, 1)
 score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FilterParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -638,8 +658,13 @@ score_filter_simt_kernel(const float* __restrict__ table, long long n_items, int
     }
 }
 
+// Per-query set-up of one search, one launch: the admission margin, the finite stand-in for "-inf", the overflow
+// guard of the scaled filter -- and the reset of the query's candidate count, overflow mark and threshold (these
+// were two memsets and a fill kernel: three more launches on a step that is ~15 launches long at small batches).
 __global__ void query_margin_kernel(const float* __restrict__ queries, int B, int d, float factor, float max_norm,
-                                    float* __restrict__ margin, float* __restrict__ floor, float* __restrict__ qmax) {
+                                    float* __restrict__ margin, float* __restrict__ floor, float* __restrict__ qmax,
+                                    unsigned int* __restrict__ cnt, unsigned int* __restrict__ ovf,
+                                    float* __restrict__ thr) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= B) return;
     float s = 0.0f, mx = 0.0f;
@@ -657,6 +682,9 @@ __global__ void query_margin_kernel(const float* __restrict__ queries, int B, in
         if (margin) margin[q] = factor * nrm;
         // no score of this query can be below -|q| * max|x| (minus the bf16 slack): a finite "-inf"
         floor[q] = -(1.01f * nrm * max_norm + 1e-30f);
+        cnt[q] = 0u;
+        ovf[q] = 0u;
+        thr[q] = __int_as_float(0xff800000);
     }
 }
 
@@ -786,9 +814,10 @@ cudaError_t launch_filter_simt(const float* table, long long n_items, int d, con
 }
 
 cudaError_t launch_query_margin(const float* queries, int B, int d, float factor, float max_norm, float* margin,
-                                float* floor, float* qmax, cudaStream_t stream) {
+                                float* floor, float* qmax, unsigned int* cnt, unsigned int* ovf, float* thr,
+                                cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, max_norm, margin, floor, qmax);
+    query_margin_kernel<<<(B + 7) / 8, 256, 0, stream>>>(queries, B, d, factor, max_norm, margin, floor, qmax, cnt, ovf, thr);
     return cudaGetLastError();
 }
 

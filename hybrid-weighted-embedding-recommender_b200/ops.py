@@ -151,7 +151,8 @@ class TopKIndex:
     def topk_sharded_async(self, exchange, queries, k, mode="exact", idx_offset=0, cap=0, want_f64=False,
                            phases=N.PHASE_ALL, out=None):
         """hwer_topk_sharded: this shard's search, the peer-memory exchange and the owner-side merge, enqueued on
-        the current stream.  Collective over the exchange's ranks; returns the global [B, k] result."""
+        the current stream.  Collective over the exchange's ranks; returns the global [B, k] result -- or, with
+        PHASE_OWNED among `phases`, only the rows of the queries this rank merged (owner_range of the exchange)."""
         queries = _need(queries, torch.float32, "queries", 2)
         if queries.shape[1] != self.d:
             raise ValueError("query width %d != table width %d" % (queries.shape[1], self.d))
@@ -159,9 +160,13 @@ class TopKIndex:
         if k > self.n:
             raise ValueError("k=%d must be less than or equal to the number of rows %d of every shard" % (k, self.n))
         if out is None:
-            idx = torch.empty((B, k), dtype=torch.int64, device=self.device)
-            score = torch.empty((B, k), dtype=torch.float32, device=self.device)
-            s64 = torch.empty((B, k), dtype=torch.float64, device=self.device) if want_f64 else None
+            rows = B
+            if int(phases) & N.PHASE_OWNED:
+                lo, hi = exchange.owner_range(B)
+                rows = hi - lo
+            idx = torch.empty((rows, k), dtype=torch.int64, device=self.device)
+            score = torch.empty((rows, k), dtype=torch.float32, device=self.device)
+            s64 = torch.empty((rows, k), dtype=torch.float64, device=self.device) if want_f64 else None
         else:
             idx, score, s64 = out
         m = N.MODE_EXACT if mode == "exact" else N.MODE_BF16 if mode == "bf16" else None

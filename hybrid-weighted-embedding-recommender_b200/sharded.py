@@ -83,6 +83,13 @@ class PeerExchange:
                                              self.device.index or 0))
         dist.barrier(group=group)          # every rank has opened every buffer before anyone stores into one
 
+    def owner_range(self, n_queries: int) -> Tuple[int, int]:
+        """[lo, hi) of the queries of a batch of `n_queries` that this rank merges (csrc/exchange.cu: contiguous
+        ranges of ceil(B / world) queries)."""
+        per = (int(n_queries) + self.world - 1) // self.world
+        lo = min(self.rank * per, int(n_queries))
+        return lo, min(lo + per, int(n_queries))
+
     def configure(self, largest_shard_rows: int, share_thresholds: bool = True):
         N.check(N.lib().hwer_exchange_configure(self._h, int(largest_shard_rows), 1 if share_thresholds else 0))
 
@@ -151,20 +158,35 @@ class ShardedTopK:
             self._px.configure(self.rows_max, self.share_thresholds)
         return self._px
 
-    def topk_p2p_async(self, queries, k, mode="exact", cap=0, want_f64=False):
-        """Enqueues the fused search + peer exchange; results are valid after `finish_p2p()`."""
+    def topk_p2p_async(self, queries, k, mode="exact", cap=0, want_f64=False, owned=False):
+        """Enqueues the fused search + peer exchange; results are valid after `index.finish()`.  owned=True: only
+        the rows of the queries this rank merged (`owner_range`), see HWER_PHASE_OWNED."""
         B, k = queries.shape[0], int(k)
         px = self._peer_exchange(B, k)
         return self.index.topk_sharded_async(px, queries, k, mode, idx_offset=self.row_offset, cap=cap,
-                                             want_f64=want_f64)
+                                             want_f64=want_f64,
+                                             phases=N.PHASE_ALL | (N.PHASE_OWNED if owned else 0))
 
-    def topk(self, queries, k, mode="exact"):
+    def owner_range(self, n_queries: int) -> Tuple[int, int]:
+        """Queries [lo, hi) whose merged result `topk(..., owned=True)` returns on this rank."""
+        n_queries = int(n_queries)
+        if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return 0, n_queries
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        per = (n_queries + world - 1) // world
+        lo = min(rank * per, n_queries)
+        return lo, min(lo + per, n_queries)
+
+    def topk(self, queries, k, mode="exact", owned=False):
+        """Global top-k of all shards.  Default: the full [B, k] result on every rank.  owned=True: every rank gets
+        the rows of `owner_range(B)` only -- each query's answer lands on exactly one rank (the form a serving tier
+        wants: 1/world of the result to copy to each host, nothing delivered twice over NVLink)."""
         k = int(k)
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
         if multi and self.exchange in ("auto", "p2p") and self.rows_min >= k and queries.is_cuda:
             cap = 0
             for _ in range(6):
-                idx, score, _ = self.topk_p2p_async(queries, k, mode, cap=cap)
+                idx, score, _ = self.topk_p2p_async(queries, k, mode, cap=cap, owned=owned)
                 # one stream synchronisation per step: the largest capacity demand of ANY rank and a peer timeout
                 # come back through the exchange buffers (csrc/exchange.cu), so every rank takes the same decision
                 # here without a host-side collective
@@ -183,7 +205,11 @@ class ShardedTopK:
         if not multi:
             return idx, s64.float()
         gs, gi = gather_shard_results(idx, s64, self.group)
-        return ops.merge_topk(gs, gi)
+        idx, score = ops.merge_topk(gs, gi)
+        if owned:
+            lo, hi = self.owner_range(queries.shape[0])
+            return idx[lo:hi], score[lo:hi]
+        return idx, score
 
     def close(self):
         if self._px is not None:

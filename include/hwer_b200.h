@@ -161,6 +161,11 @@ int hwer_exchange_destroy(hwer_exchange_t* exchange);
 #define HWER_PHASE_MERGE 2   /* wait for every source, merge the owned queries, deliver to every rank, publish      */
 #define HWER_PHASE_COLLECT 4 /* wait for every owner, copy the [B, k] result into out_*                             */
 #define HWER_PHASE_ALL 7     /* the normal call; a host may also enqueue the phases one by one, in this order       */
+#define HWER_PHASE_OWNED 8   /* modifier (pass it with MERGE and COLLECT): every rank keeps only the queries it merged:
+                              * out_* receive rows [rank * ceil(B / world), ...) of the result, packed from row 0 (the
+                              * "reduce-scatter" form of the exchange: a serving tier that answers from all ranks needs
+                              * each result once, so winners are not delivered to the other ranks and a rank copies 1/world
+                              * of the result to its host)                                                           */
 int hwer_topk_sharded(hwer_index_t* index, hwer_exchange_t* exchange, const float* queries_dev, int32_t B, int32_t k,
                       int32_t mode, uint32_t cap, int64_t idx_offset, int64_t* out_idx_dev, float* out_score_dev,
                       double* out_score64_dev, int32_t phases, void* stream);

@@ -458,6 +458,21 @@ def test_peer_exchange_protocol_on_one_gpu(hw, world, B, k, share):
                 N.check(lib.hwer_exchange_error(ex[r]._h, None))
                 assert torch.equal(outs[r][0], ref_idx), "rank %d rows differ" % r
                 assert torch.equal(outs[r][2], ref_s64) and torch.equal(outs[r][1], ref_sc)
+            # HWER_PHASE_OWNED: every rank keeps only the queries it merged, packed from row 0 of its outputs
+            per = (B + world - 1) // world
+            for o in outs:
+                o[0].fill_(-7)
+            for phase in (N.PHASE_SEARCH, N.PHASE_MERGE | N.PHASE_OWNED, N.PHASE_COLLECT | N.PHASE_OWNED):
+                for r in range(world):
+                    with torch.cuda.stream(streams[r]):
+                        shards[r][0].topk_sharded_async(ex[r], q, k, idx_offset=shards[r][1], phases=phase, out=outs[r])
+            torch.cuda.synchronize()
+            for r in range(world):
+                N.check(lib.hwer_exchange_error(ex[r]._h, None))
+                lo, hi = min(r * per, B), min((r + 1) * per, B)
+                assert torch.equal(outs[r][0][:hi - lo], ref_idx[lo:hi]), "rank %d owned rows differ" % r
+                assert torch.equal(outs[r][2][:hi - lo], ref_s64[lo:hi]) and torch.equal(outs[r][1][:hi - lo], ref_sc[lo:hi])
+                assert bool((outs[r][0][hi - lo:] == -7).all()), "rank %d wrote past its owned rows" % r
     finally:
         torch.cuda.synchronize()
         for r in range(world):
@@ -488,6 +503,10 @@ def _p2p_worker(rank, world, port, out_dir):
         for _ in range(2):
             idx, sc = sh.topk(q, k)
         res[ex] = (idx.cpu(), sc.cpu())
+        # owned=True: each rank gets exactly the rows of the queries it merged
+        lo, hi = sh.owner_range(B)
+        oidx, osc = sh.topk(q, k, owned=True)
+        assert oidx.shape[0] == hi - lo and torch.equal(oidx.cpu(), res[ex][0][lo:hi]) and torch.equal(osc.cpu(), res[ex][1][lo:hi])
         sh.close()
     whole_idx, whole_sc = hwm.ops.TopKIndex(table).topk(q, k)
     assert torch.equal(res["p2p"][0], whole_idx.cpu()) and torch.equal(res["nccl"][0], whole_idx.cpu())
