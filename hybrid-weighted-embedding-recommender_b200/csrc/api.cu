@@ -198,6 +198,9 @@ int make_schedule(const hwer_index* ix, int B, int k, unsigned int cap_user, int
     // round 0 must leave every list with the k candidates its select needs (shards that share thresholds publish
     // their ceil(k / G)-th best, so they need that many)
     const long long k_need = world_share > 1 ? (k + world_share - 1) / world_share : k;
+    // sharing shards see the union of G round-0 samples: a shorter dense round gives the same first bound
+    if (world_share >= 8 && B > 512) first_rows = 2048;
+    if (world_share > 1 && B > 16 && B <= 128) first_rows = 2048;
     if (first_rows < 2LL * k_need) first_rows = 2LL * k_need;
     if (ix->env_first_rows >= 2LL * k_need && ix->env_first_rows <= max_cap) first_rows = ix->env_first_rows;   // tuning knob
     s->first_tiles = (first_rows + hwer::kTileItems - 1) / hwer::kTileItems;
@@ -216,9 +219,13 @@ int make_schedule(const hwer_index* ix, int B, int k, unsigned int cap_user, int
     // Item shards that share thresholds every round (hwer_topk_sharded) each admit ~1/G of a round's candidates, so
     // their rounds can grow G times faster for the same lists: a 1.25 M-row shard of an 8-way split needs 3 filter
     // launches instead of 7, and every launch saved is ~100 us of extract + select + exchange on a ~2 ms step.
+    // Measured on 2 / 4 / 8 B200 (scripts/tune_schedule_sharded.py, profiles/r02_k_tune_n*.txt): the growth that pays
+    // stops at 8 for large batches (10 M rows over 8 GPUs, B = 4096: 1.40 ms per step at growth 8 after a 2048-row
+    // round 0, 1.55 ms at 16 after 4096 rows) and at 32 for small ones.
     if (world_share > 1 && ix->env_growth < 1) {
         long long ge = (long long)g * world_share;
-        g = (int)(ge > 64 ? 64 : ge);
+        const long long g_max = B > 512 ? 8 : (B > 128 ? 64 : 32);
+        g = (int)(ge > g_max ? g_max : ge);
     }
     s->growth = g;
     s->late_tiles = 1LL << 40;            // optional switch to plain doubling once this many tiles have been seen

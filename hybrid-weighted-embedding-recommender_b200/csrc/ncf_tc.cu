@@ -304,6 +304,42 @@ cudaError_t launch_ncf_score_tc(const float* h, long long n_rows, int F, int dep
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
+    // Tensor maps depend on the scratch layout only (ping-pong activation arrays of `chunk` rows, split weights), not
+    // on the chunk being processed: encode them ONCE per call.  (r2: encoding 12 maps per chunk made the chunk loop
+    // host-bound -- 5.0 ms per 819 K pairs of which 2.5 ms were kernels.)  A short last chunk reuses them: the layer
+    // kernels only touch the first p_pad / 128 row tiles, and the gather zero-fills [pc, p_pad).
+    struct LayerPlan { NcfLayerParams q; CUtensorMap mxh, mxl, mwh, mwl; size_t smem; bool last; };
+    LayerPlan plan[16];
+    if (depth > 16) return cudaErrorInvalidValue;
+    {
+        size_t w_off = 0;
+        int cur = 0;
+        for (int l = 1; l <= depth; ++l) {
+            LayerPlan& L = plan[l - 1];
+            const int in = ncf_layer_in(F, depth, l), outw = ncf_layer_out(F, depth, l);
+            L.last = l == depth;
+            NcfLayerParams& q = L.q;
+            memset(&q, 0, sizeof q);
+            q.n_tile = outw < 256 ? outw : 256;
+            q.n_tiles = outw / q.n_tile;
+            q.in = in; q.out = outw; q.slope = 0.01f;
+            q.bias = params + w_off + (size_t)in * outw;
+            q.stages = 2;
+            while (q.stages < 6 && ncf_tc_smem_bytes(q.n_tile, q.stages + 1) <= (size_t)kSmemBudget) ++q.stages;
+            if (!ncf_tensor_map(&L.mxh, xh[cur], chunk, in, kNcfM) || !ncf_tensor_map(&L.mxl, xl[cur], chunk, in, kNcfM) ||
+                !ncf_tensor_map(&L.mwh, wh + w_off, outw, in, q.n_tile) || !ncf_tensor_map(&L.mwl, wl + w_off, outw, in, q.n_tile))
+                return cudaErrorInvalidValue;
+            L.smem = ncf_tc_smem_bytes(q.n_tile, q.stages);
+            if (L.last) {
+                q.w_out = params + w_off + (size_t)in * outw + outw;
+                q.b_out = q.w_out + F;
+            } else {
+                q.y_hi = xh[cur ^ 1]; q.y_lo = xl[cur ^ 1];
+            }
+            w_off += (size_t)in * outw + outw;
+            cur ^= 1;
+        }
+    }
     for (long long p0 = 0; p0 < P; p0 += chunk) {
         const long long pc = P - p0 < chunk ? P - p0 : chunk;
         const long long p_pad = (pc + kNcfM - 1) / kNcfM * kNcfM;
@@ -313,40 +349,20 @@ cudaError_t launch_ncf_score_tc(const float* h, long long n_rows, int F, int dep
             if (blocks > 148LL * 16) blocks = 148LL * 16;
             ncf_gather_split_kernel<<<(int)blocks, 256, 0, stream>>>(h, n_rows, F, src + p0, dst + p0, pc, p_pad, xh[0], xl[0]);
         }
-        size_t w_off = 0;
-        int cur = 0;
         for (int l = 1; l <= depth; ++l) {
-            const int in = ncf_layer_in(F, depth, l), outw = ncf_layer_out(F, depth, l);
-            const bool last = l == depth;
-            NcfLayerParams q;
-            memset(&q, 0, sizeof q);
+            LayerPlan& L = plan[l - 1];
+            NcfLayerParams q = L.q;
             q.p_rows = pc; q.m_tiles = (int)(p_pad / kNcfM);
-            q.n_tile = outw < 256 ? outw : 256;
-            q.n_tiles = outw / q.n_tile;
-            q.in = in; q.out = outw; q.slope = 0.01f;
-            q.bias = params + w_off + (size_t)in * outw;
-            q.stages = 2;
-            while (q.stages < 6 && ncf_tc_smem_bytes(q.n_tile, q.stages + 1) <= (size_t)kSmemBudget) ++q.stages;
-            CUtensorMap mxh, mxl, mwh, mwl;
-            if (!ncf_tensor_map(&mxh, xh[cur], p_pad, in, kNcfM) || !ncf_tensor_map(&mxl, xl[cur], p_pad, in, kNcfM) ||
-                !ncf_tensor_map(&mwh, wh + w_off, outw, in, q.n_tile) || !ncf_tensor_map(&mwl, wl + w_off, outw, in, q.n_tile))
-                return cudaErrorInvalidValue;
-            const size_t smem = ncf_tc_smem_bytes(q.n_tile, q.stages);
             const int items = q.m_tiles * q.n_tiles;
             const int grid = items < num_sms ? items : num_sms;
-            if (last) {
-                q.w_out = params + w_off + (size_t)in * outw + outw;
-                q.b_out = q.w_out + F;
+            if (L.last) {
                 q.score = out + p0;
-                ncf_layer_tc_kernel<true><<<grid, kNcfThreads, smem, stream>>>(mxh, mxl, mwh, mwl, q);
+                ncf_layer_tc_kernel<true><<<grid, kNcfThreads, L.smem, stream>>>(L.mxh, L.mxl, L.mwh, L.mwl, q);
             } else {
-                q.y_hi = xh[cur ^ 1]; q.y_lo = xl[cur ^ 1];
-                ncf_layer_tc_kernel<false><<<grid, kNcfThreads, smem, stream>>>(mxh, mxl, mwh, mwl, q);
+                ncf_layer_tc_kernel<false><<<grid, kNcfThreads, L.smem, stream>>>(L.mxh, L.mxl, L.mwh, L.mwl, q);
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
-            w_off += (size_t)in * outw + outw;
-            cur ^= 1;
         }
     }
     return cudaSuccess;

@@ -12,6 +12,7 @@
 //   merge          : G shards x K -> K with the same ordering rule (multi-GPU).
 //
 // One CTA per query; lists are sorted in shared memory with a bitonic network.
+#include <cstdlib>
 #include <cstring>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -207,6 +208,164 @@ select_compact_kernel(unsigned long long* __restrict__ cand, unsigned int* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same selection with the keys held in REGISTERS and the K-th best found by BISECTION on the 32-bit score image
+// (r2).  f(v) = #{keys with image >= v} is monotone, so the K-th largest image is the largest v with f(v) >= K:
+// at most 32 steps of "compare my keys with the pivot, add up" -- per step a handful of integer compares per thread
+// and ONE block-wide sum, against four radix passes of shared-memory histogram atomics over a staged copy of the
+// list (heavily conflicting in the first pass: all scores of a query share their top byte).  The answer is the same
+// number the radix select returns, so thresholds, candidate lists and results are bit-identical.
+template <int KPT>      // keys per thread: the CTA handles lists of up to kSelThreads * KPT keys (the launcher checks cap)
+__global__ void __launch_bounds__(kSelThreads)
+select_compact_bisect_kernel(unsigned long long* __restrict__ cand, unsigned int* __restrict__ cnt, unsigned int cap,
+                             int K, int fixed_count, const float* __restrict__ margin, float* __restrict__ thr,
+                             unsigned int* needed_cap, unsigned int* __restrict__ ovf,
+                             const __grid_constant__ SelExchange sx) {
+    __shared__ unsigned int step_cnt[36];            // one counter per bisection step (never reset inside the loop)
+    __shared__ unsigned int kept_s, valid_s, max_s;
+    __shared__ float global_kth_s;
+    const int q = blockIdx.x;
+    const bool shared = sx.mode == kSelShared;
+    if (shared) K = sx.k_share;                       // what this shard publishes: its ceil(k / G)-th best
+    unsigned int c_raw = fixed_count >= 0 ? (unsigned int)fixed_count : cnt[q];
+    if (c_raw > cap) {
+        if (threadIdx.x == 0) { atomicMax(needed_cap, c_raw); ovf[q] = 1u; }
+        c_raw = cap;
+    }
+    const int c = (int)c_raw;
+    unsigned long long* list = cand + (size_t)q * cap;
+    if (threadIdx.x < 36) step_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) { kept_s = 0u; valid_s = 0u; max_s = 0u; }
+    __syncthreads();
+    unsigned long long key[KPT];
+    unsigned int nvalid = 0u, vmax = 0u;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        const int i = (int)threadIdx.x + j * kSelThreads;
+        key[j] = i < c ? list[i] : 0ull;             // key 0 = empty slot of a dense round (tail rows, NaN scores)
+        const unsigned int hi = (unsigned int)(key[j] >> 32);
+        nvalid += key[j] != 0ull ? 1u : 0u;
+        vmax = hi > vmax ? hi : vmax;
+    }
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane_id() == 0) { if (nvalid) atomicAdd(&valid_s, nvalid); atomicMax(&max_s, vmax); }
+    __syncthreads();
+    float t = __int_as_float(0xff800000);   // -inf: fewer than K candidates so far, admit everything
+    float sk = t;                           // the K-th best score of the list
+    if ((int)valid_s >= K) {
+        // invariant: f(lo) >= K.  Every valid key's image is >= 1 (0 is the empty key), f(1) = valid_s.
+        unsigned int lo = 1u, hi = max_s;
+        int step = 0;
+        while (lo < hi) {                   // block-uniform: lo / hi derive from shared counters only
+            const unsigned int mid = lo + ((hi - lo + 1u) >> 1);
+            unsigned int n = 0u;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) n += (unsigned int)(key[j] >> 32) >= mid ? 1u : 0u;
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (lane_id() == 0 && n) atomicAdd(&step_cnt[step], n);
+            __syncthreads();
+            if (step_cnt[step] >= (unsigned int)K) lo = mid; else hi = mid - 1u;
+            ++step;
+        }
+        sk = ordered_to_f32(lo);
+    }
+    if (shared) {                                     // publish first, then wait: no shard ever waits on a waiter
+        if (threadIdx.x == 0) sel_publish_kth(sx, sx.q0 + q, sk);       // -inf = "cannot bound yet"
+        if (threadIdx.x < 32) {
+            const float g = sel_wait_global_kth(sx, sx.q0 + q, threadIdx.x);
+            if (threadIdx.x == 0) global_kth_s = g;
+        }
+        __syncthreads();
+        sk = global_kth_s;                            // lower bound of the global k-th best score
+    }
+    if (sk > __int_as_float(0xff800000)) {
+        const float m = margin ? margin[q] : 0.0f;
+        t = sk - m;
+        if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);   // absorb the rounding of the subtraction itself
+    }
+    // every key is in a register by now, so compacting in place cannot overwrite an unread one
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        if (j * kSelThreads < c) {                    // block-uniform: whole warps take part in the ballot
+            const unsigned long long k = key[j];
+            const bool keep = k != 0ull && key_score(k) >= t;
+            const unsigned int m = __ballot_sync(0xffffffffu, keep);       // one slot-allocating atomic per warp
+            unsigned int slot = 0u;
+            if (lane_id() == 0 && m) slot = atomicAdd(&kept_s, (unsigned int)__popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (keep) list[slot + __popc(m & ((1u << lane_id()) - 1u))] = k;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cnt[q] = kept_s;
+        thr[q] = t;
+    }
+}
+
+// ONE WARP per query, keys in registers (lists of up to 32 * kSelWarpRegKeys keys; longer ones take the radix path of
+// select_compact_warp_kernel's body below): per bisection step a lane compares its keys with the pivot and one
+// warp-wide integer add (REDUX) gives every lane the count -- no shared memory, no atomics, no barrier.
+constexpr int kSelWarpRegKeys = 32;
+
+template <int KPL>
+__device__ __forceinline__ void select_warp_bisect(unsigned long long* __restrict__ glist, int c, int K, int q, int l,
+                                                   const float* __restrict__ margin, float* __restrict__ thr,
+                                                   unsigned int* __restrict__ cnt, const SelExchange& sx, bool shared) {
+    unsigned long long key[KPL];
+    unsigned int nvalid = 0u, vmax = 0u;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const int i = l + 32 * j;
+        key[j] = i < c ? glist[i] : 0ull;
+        const unsigned int hi = (unsigned int)(key[j] >> 32);
+        nvalid += key[j] != 0ull ? 1u : 0u;
+        vmax = hi > vmax ? hi : vmax;
+    }
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    float t = __int_as_float(0xff800000);
+    float sk = t;
+    if ((int)nvalid >= K) {
+        unsigned int lo = 1u, hi = vmax;
+        while (lo < hi) {
+            const unsigned int mid = lo + ((hi - lo + 1u) >> 1);
+            unsigned int n = 0u;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) n += (unsigned int)(key[j] >> 32) >= mid ? 1u : 0u;
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (n >= (unsigned int)K) lo = mid; else hi = mid - 1u;
+        }
+        sk = ordered_to_f32(lo);
+    }
+    if (shared) {
+        if (l == 0) sel_publish_kth(sx, sx.q0 + q, sk);
+        __syncwarp();
+        sk = sel_wait_global_kth(sx, sx.q0 + q, l);
+    }
+    if (sk > __int_as_float(0xff800000)) {
+        const float m = margin ? margin[q] : 0.0f;
+        t = sk - m;
+        if (m > 0.0f) t -= 1e-6f * (fabsf(sk) + m);
+    }
+    unsigned int kept = 0u;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        if (32 * j < c) {                                           // warp-uniform
+            const unsigned long long k = key[j];
+            const bool keep = k != 0ull && key_score(k) >= t;
+            const unsigned int m = __ballot_sync(0xffffffffu, keep);
+            if (keep) glist[kept + __popc(m & ((1u << l) - 1u))] = k;      // order-preserving, in place
+            kept += __popc(m);
+        }
+    }
+    if (l == 0) {
+        cnt[q] = kept;
+        thr[q] = t;
+    }
+}
+
 // The same selection with ONE WARP per query, for the filter rounds of large batches: their lists are short
 // (about k * (1 + 1.4 growth) keys), so a CTA per query spends its time in __syncthreads and leaves most of the
 // machine idle, while thousands of independent warps finish in one wave.  The list is re-read from L1/L2 in every
@@ -234,6 +393,12 @@ select_compact_warp_kernel(unsigned long long* __restrict__ cand, unsigned int* 
     }
     const int c = (int)c_raw;
     unsigned long long* glist = cand + (size_t)q * cap;
+    if (c <= 32 * kSelWarpRegKeys) {                  // the normal case: keys in registers, bisection (see below)
+        if (c <= 32 * 8) select_warp_bisect<8>(glist, c, K, q, l, margin, thr, cnt, sx, shared);
+        else if (c <= 32 * 16) select_warp_bisect<16>(glist, c, K, q, l, margin, thr, cnt, sx, shared);
+        else select_warp_bisect<kSelWarpRegKeys>(glist, c, K, q, l, margin, thr, cnt, sx, shared);
+        return;
+    }
     // the list lives in shared memory when it fits (the normal case), else it is read through L2 every pass
     const bool staged = c <= kSelWarpKeys;
     volatile unsigned long long* list = staged ? keys_all[w] : glist;
@@ -778,6 +943,19 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
     }
     // stage only what can be there: a dense round holds fixed_count keys, a filter round at most cap
     const size_t n = fixed_count >= 0 ? (size_t)fixed_count : (size_t)cap;
+    static const bool radix_only = getenv("HWER_SELECT_RADIX") != nullptr;      // A/B knob, read once
+    if (!radix_only && n <= (size_t)kSelThreads * 64) {
+        // keys in registers + bisection (bit-identical thresholds); KPT sized to what the list can hold
+#define HWER_SEL_BISECT(KPT)                                                                                          \
+        select_compact_bisect_kernel<KPT><<<B, kSelThreads, 0, stream>>>(cand, cnt, cap, K, fixed_count, margin, thr, \
+                                                                         needed_cap, ovf, sx)
+        if (n <= (size_t)kSelThreads * 8) HWER_SEL_BISECT(8);
+        else if (n <= (size_t)kSelThreads * 16) HWER_SEL_BISECT(16);
+        else if (n <= (size_t)kSelThreads * 32) HWER_SEL_BISECT(32);
+        else HWER_SEL_BISECT(64);
+#undef HWER_SEL_BISECT
+        return cudaGetLastError();
+    }
     const size_t smem = (n < 1024 ? 1024 : n) * sizeof(unsigned long long);
     cudaError_t e = set_smem(select_compact_kernel, smem);
     if (e != cudaSuccess) return e;
