@@ -88,7 +88,10 @@ struct hwer_index {
     // HWER_DISABLE bit mask for A/B runs (measured in profiles/r02_*_ab.txt): 1 = bias MMA instead of scaled queries,
     // 2 = only the full-capacity final shape; and three alternatives that measured no better and are off by default:
     // 4 = warp-per-query final, 8 = spill extraction fused into the filter kernel, 16 = warp-per-query dense select;
-    // 32 = no extra CTAs on the SMs left over by slots * query blocks
+    // 32 = ENABLE extra CTAs on the SMs left over by slots * query blocks (148 - 9 * 16 = 4 at B = 4096).  Built and
+    // measured in r2 (profiles/r02_s_ab_extra_ctas.txt): the four extra CTAs walk the tail tiles once per query block,
+    // out of step with everyone else -- DRAM reads per step rose from 3.1 to 4.4 GB, the mid rounds got 10-20 % slower
+    // and the long round did not change, so the grid stays at slots * query blocks (144 CTAs) by default
     int env_disable = 0;
     // optional live profiling of the dominant (filter) kernel with CUDA events on the launching stream
     bool prof = false;
@@ -429,7 +432,7 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 p.dense = round == 0 ? 1 : 0;      // open threshold: positional writes, no atomics
                 p.spill = ix->spill; p.spill_cnt = ix->spill_cnt; p.spill_cap = ix->spill_cap; p.spill_ctas = ix->num_sms;
                 p.fused_extract = (ix->env_disable & 8) ? 1 : 0;
-                p.no_extra_ctas = (ix->env_disable & 32) ? 1 : 0;
+                p.no_extra_ctas = (ix->env_disable & 32) ? 0 : 1;
                 HWER_CUDA(hwer::launch_filter_tc(ix->tmap, p, ix->num_sms, stream));
                 if (round > 0 && !p.fused_extract) ix->other_launches += 1;     // spill_extract_kernel behind the filter
             } else {
