@@ -470,6 +470,7 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         // ---- stage the query block: fp32 (x 1 / thr in a scaled block) -> bf16 (RN), K-major, 128B swizzle ----
         {
             constexpr int chunks_per_row = KB * 8;   // 16-byte chunks (8 bf16) per query row
+            const bool q_vec = (p.d & 7) == 0 && (reinterpret_cast<uintptr_t>(p.queries) & 15u) == 0;
             for (int i = threadIdx.x; i < nq * chunks_per_row; i += kThreadsTc) {
                 const int r = i / chunks_per_row;
                 const int c = i - r * chunks_per_row;
@@ -477,10 +478,17 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 // two fp32 roundings (reciprocal, product): 2^-23 relative, inside the margin's slack (kernels.h)
                 const float scale = (scaled && q < p.B) ? 1.0f / thr_s[r] : 1.0f;
                 float f[8];
+                if (q_vec && q < p.B && c * 8 < p.d) {        // whole 8-column chunk inside the row: two 128-bit loads
+                    const float4* src = reinterpret_cast<const float4*>(p.queries + (size_t)q * p.d + c * 8);
+                    const float4 lo4 = __ldg(src), hi4 = __ldg(src + 1);
+                    f[0] = lo4.x * scale; f[1] = lo4.y * scale; f[2] = lo4.z * scale; f[3] = lo4.w * scale;
+                    f[4] = hi4.x * scale; f[5] = hi4.y * scale; f[6] = hi4.z * scale; f[7] = hi4.w * scale;
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = c * 8 + j;
-                    f[j] = (q < p.B && col < p.d) ? __ldg(p.queries + (size_t)q * p.d + col) * scale : 0.0f;
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = c * 8 + j;
+                        f[j] = (q < p.B && col < p.d) ? __ldg(p.queries + (size_t)q * p.d + col) * scale : 0.0f;
+                    }
                 }
                 uint4 pk;
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]);
