@@ -328,8 +328,27 @@ class RecommendationBase(metaclass=abc.ABCMeta):
         return edges
 
     # ------------------------------------------------------------------ pair scores
+    def _rows_to_device(self, rows) -> torch.Tensor:
+        """A Python list of rows -> int64 device tensor through a pinned staging buffer (grow-only, reused): numpy
+        fills it in one pass and the copy is asynchronous -- torch.tensor(list, device=...) walks the list
+        element by element and copies from pageable memory (0.23 ms for 4096 rows, profiles/r02_q_time_api.txt)."""
+        n = len(rows)
+        st = getattr(self, "_row_staging", None)
+        if st is None or st.shape[0] < n:
+            st = torch.empty((max(n, 4096),), dtype=torch.int64).pin_memory()
+            self._row_staging = st
+            self._row_staging_ev = None
+        elif self._row_staging_ev is not None:
+            self._row_staging_ev.synchronize()          # the previous upload has left the buffer
+        st.numpy()[:n] = np.fromiter(rows, dtype=np.int64, count=n)
+        dev = self.device_vectors.device
+        out = st[:n].to(dev, non_blocking=True)
+        self._row_staging_ev = torch.cuda.Event()
+        self._row_staging_ev.record(torch.cuda.current_stream(dev))
+        return out
+
     def _rows_of(self, nodes) -> torch.Tensor:
-        return torch.tensor(self.nodes_to_idx.rows_of(nodes), dtype=torch.int64, device=self.device_vectors.device)
+        return self._rows_to_device(self.nodes_to_idx.rows_of(nodes))
 
     def predict_rows(self, src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
         return ops.pair_score(self.device_vectors, src_rows, dst_rows)
@@ -418,7 +437,7 @@ class RecommendationBase(metaclass=abc.ABCMeta):
             rows = self.nodes_to_idx.rows_of(anchors)
             if rows and min(rows) < 0:
                 raise NodeNotFoundException("Node = %s, was not provided in training" % anchors[rows.index(min(rows))])
-            anchor_rows = torch.tensor(rows, dtype=torch.int64, device=self.device_vectors.device)
+            anchor_rows = self._rows_to_device(rows)
         pos = self._csr_rows(positive) if positive is not None and any(positive) else None
         neg = self._csr_rows(negative) if negative is not None and any(negative) else None
         queries = ops.compose_queries(self.device_vectors, anchor_rows, pos, neg)
