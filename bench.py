@@ -238,7 +238,7 @@ def run_reference(a):
 def make_shard(hw, torch, a, begin, end, dev):
     """Rows [begin, end) of the global table V = unit(alpha unit(C) + (1-alpha) unit(G)); chunk c of CHUNK rows is
     generated from seeds (c, 10^6 + c), so the catalogue does not depend on the shard count.  The blend+normalise
-    kernel is timed on the whole shard in one launch (after one untimed call)."""
+    kernel is timed on the whole shard (best of three launches after one untimed call)."""
     rows = end - begin
     content = torch.empty((rows, a.dim), dtype=torch.float32, device=dev)
     collab = torch.empty((rows, a.dim), dtype=torch.float32, device=dev)
@@ -254,13 +254,15 @@ def make_shard(hw, torch, a, begin, end, dev):
         del cc, gg
     table, shadow = hw.ops.blend_normalize(content, collab, a.alpha)
     torch.cuda.synchronize()
-    del table, shadow
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    table, shadow = hw.ops.blend_normalize(content, collab, a.alpha)
-    e1.record()
-    torch.cuda.synchronize()
-    blend_ms = e0.elapsed_time(e1)
+    blend_ms = float("inf")
+    for _ in range(3):                               # best of three whole-shard launches, like MEASURED_PEAKS' copy figure
+        del table, shadow
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        table, shadow = hw.ops.blend_normalize(content, collab, a.alpha)
+        e1.record()
+        torch.cuda.synchronize()
+        blend_ms = min(blend_ms, e0.elapsed_time(e1))
     blend_bytes = rows * a.dim * (4 + 4 + 4) + rows * shadow.shape[1] * 2
     del content, collab
     return table, shadow, blend_ms, blend_bytes

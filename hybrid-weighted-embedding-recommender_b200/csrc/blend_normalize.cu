@@ -11,6 +11,8 @@
 //
 // One warp per row, 128-bit coalesced loads, rows held in registers between
 // the norm pass and the write pass (no second read from HBM).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,10 +32,12 @@ __device__ __forceinline__ void store_bf16_row_chunk(__nv_bfloat16* dst, const f
     stg_stream_u2(reinterpret_cast<uint2*>(dst), u);
 }
 
-// VEC = float4 per lane (d4 = d/4 <= 32*VEC).  HAS_C: blend with a content row.  A warp works on kRowsPerWarp (2) rows at
+// VEC = float4 per lane (d4 = d/4 <= 32*VEC).  HAS_C: blend with a content row.  A warp works on kRowsPerWarp rows at
 // a time: all their loads are issued before the first reduction, so a lane has 2 * VEC * kRowsPerWarp 128-bit loads
-// in flight (one row per warp left the kernel at 0.85 of copy bandwidth: too few bytes in flight per SM).
-template <int VEC, bool HAS_C, int kRowsPerWarp = (VEC <= 2 ? 2 : 1)>     // wider rows: registers allow one row
+// in flight.  Measured at 10 M x 128 (scripts/tune_blend.py, profiles/r02_w_tune_blend.txt, best of 5 launches):
+// one row per warp 5.10-5.98 TB/s, two 5.94-6.37, four rows with 32 CTAs per SM 6.50 TB/s = 0.99 of the copy bandwidth
+// measured in the same process.
+template <int VEC, bool HAS_C, int kRowsPerWarp = (VEC == 1 ? 4 : (VEC == 2 ? 2 : 1))>   // wider rows: fewer fit registers
 __global__ void __launch_bounds__(kRowThreads)
 blend_normalize_vec_kernel(const float* __restrict__ content, const float* __restrict__ collab, float alpha,
                            const float* __restrict__ alpha_rows, long long n, int d, float* __restrict__ out_f32,
@@ -236,9 +240,16 @@ make_shadow_kernel(const float* __restrict__ table, long long n, int d, __nv_bfl
     }
 }
 
+// A/B knobs, read once (scripts/tune_blend.py): rows a warp keeps in flight, CTAs per SM of the persistent grid
+int blend_knob(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int row_grid(long long n) {
     long long blocks = (n + (kRowThreads / 32) - 1) / (kRowThreads / 32);
-    const long long cap = 148LL * 16;   // 16 resident 256-thread CTAs per SM keep enough loads in flight
+    static const int ctas_per_sm = blend_knob("HWER_BLEND_CTAS", 32);
+    const long long cap = 148LL * ctas_per_sm;   // grid-stride over 32 CTAs per SM (8 resident at a time)
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
@@ -259,6 +270,16 @@ cudaError_t launch_blend_normalize(const float* content, const float* collab, fl
         return cudaGetLastError();
     }
     const int vec = (d / 4 + 31) / 32;
+    static const int rpw = blend_knob("HWER_BLEND_RPW", 0);      // 0 = the kernel's default (2 rows for d <= 256)
+#define HWER_LAUNCH_BLEND_R(V, R)                                                                              \
+    if (content)                                                                                               \
+        blend_normalize_vec_kernel<V, true, R><<<grid, kRowThreads, 0, stream>>>(content, collab, alpha,        \
+                                                                                alpha_rows, n, d, out_f32,     \
+                                                                                out_bf16, d_pad);              \
+    else                                                                                                       \
+        blend_normalize_vec_kernel<V, false, R><<<grid, kRowThreads, 0, stream>>>(content, collab, alpha,       \
+                                                                                 alpha_rows, n, d, out_f32,    \
+                                                                                 out_bf16, d_pad);
 #define HWER_LAUNCH_BLEND(V)                                                                                   \
     if (content)                                                                                               \
         blend_normalize_vec_kernel<V, true><<<grid, kRowThreads, 0, stream>>>(content, collab, alpha, alpha_rows, \
@@ -267,6 +288,10 @@ cudaError_t launch_blend_normalize(const float* content, const float* collab, fl
         blend_normalize_vec_kernel<V, false><<<grid, kRowThreads, 0, stream>>>(content, collab, alpha,          \
                                                                               alpha_rows, n, d, out_f32,       \
                                                                               out_bf16, d_pad);
+    if (vec == 1 && (rpw == 1 || rpw == 2)) {
+        if (rpw == 1) { HWER_LAUNCH_BLEND_R(1, 1) } else { HWER_LAUNCH_BLEND_R(1, 2) }
+        return cudaGetLastError();
+    }
     switch (vec) {
         case 1: HWER_LAUNCH_BLEND(1) break;
         case 2: HWER_LAUNCH_BLEND(2) break;
@@ -274,6 +299,7 @@ cudaError_t launch_blend_normalize(const float* content, const float* collab, fl
         default: HWER_LAUNCH_BLEND(4) break;
     }
 #undef HWER_LAUNCH_BLEND
+#undef HWER_LAUNCH_BLEND_R
     return cudaGetLastError();
 }
 
