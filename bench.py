@@ -534,6 +534,10 @@ def run_b200(a):
         if exchange_note:
             line["config"]["exchange_note"] = exchange_note
         if world == 1 and a.workload == "c4" and not a.no_extras:
+            try:
+                line["aux_kernels"] = aux_kernels(hw, torch, table, pk, dev)
+            except Exception as ex:
+                line["aux_kernels"] = {"error": str(ex)[:200]}
             # summary blocks of the other single-GPU configs (full lines: --workload c3 / c2)
             try:
                 c3 = run_c3(a, hw, torch, dist, dev, 1, 0, steps=max(3, a.steps // 4), cpu=False)
@@ -672,6 +676,47 @@ def run_c3(a, hw, torch, dist, dev, world, rank, steps=None, cpu=True):
 
 
 # --------------------------------------------------------------------------------------------- C2: full validation pass
+def aux_kernels(hw, torch, table, pk, dev):
+    """Roofline lines of the gather kernels next to the search (SURVEY 8d names HBM for them): pair scores
+    (`predict`), query composition with positive / negative lists, row gathers -- random 512-byte rows of the 10 M x 128
+    table, so the ceiling is HBM's random-row rate, reported against the measured copy bandwidth.  Device-timed, best
+    of five launches each."""
+    n, d = table.shape
+    g = torch.Generator(device=dev).manual_seed(9)
+    P = 1 << 22
+    src = torch.randint(0, n, (P,), generator=g, device=dev)
+    dst = torch.randint(0, n, (P,), generator=g, device=dev)
+    B = 1 << 16
+    anchors = torch.randint(0, n, (B,), generator=g, device=dev)
+    ptr = torch.arange(0, 4 * B + 1, 4, dtype=torch.int64, device=dev)
+    pos = (ptr, torch.randint(0, n, (4 * B,), generator=g, device=dev))
+    neg = (ptr, torch.randint(0, n, (4 * B,), generator=g, device=dev))
+
+    def best(fn):
+        fn()
+        torch.cuda.synchronize()
+        ms = float("inf")
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = min(ms, e0.elapsed_time(e1))
+        return ms
+
+    out = {}
+    for name, fn, byt in (
+            ("pair_score", lambda: hw.ops.pair_score(table, src, dst), P * (2 * d * 4 + 16 + 4)),
+            ("compose_queries", lambda: hw.ops.compose_queries(table, anchors, pos, neg), B * (9 * d * 4 + d * 4 + 72)),
+            ("gather_rows", lambda: hw.ops.gather_rows(table, src[:1 << 20]), (1 << 20) * (2 * d * 4 + 8))):
+        ms = best(fn)
+        out[name] = {"ms": ms, "achieved": byt / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": byt / (ms * 1e-3) / 1e9 / pk["hbm"], "bound": "hbm (random 512-byte rows)",
+                     "algorithmic_bytes": byt}
+    return out
+
+
 def run_c2(a, hw, torch, dev):
     """BASELINE.json configs[1]: ML-1M shape (6,040 users x 3,706 items, d = 128): one validation.extraction_efficiency
     call end to end -- top-200 for every edge source, train-item filter, Recall@K / NDCG / diversity on the device,
