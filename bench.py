@@ -493,7 +493,8 @@ def run_b200(a):
     sweep = {}
     if a.sweep:
         for B in [int(x) for x in a.sweep.split(",") if x]:
-            st = max(a.steps, 20)
+            # small batches are ~0.5 ms steps: 200 of them, so that the timed region (0.1 s) is not a clock ramp
+            st = max(a.steps, 200 if B <= 256 else 20)
             sms, sf, _, _, _ = measure(B, st, a.warmup, profile=False)
             _, sf, _, _, _ = measure(B, st, 1, profile=True)
             r = roofline(B, sf / st)
