@@ -1013,7 +1013,10 @@ cudaError_t launch_select_compact(unsigned long long* cand, unsigned int* cnt, u
     if (sxp) sx = *sxp; else memset(&sx, 0, sizeof sx);
     // large batches: one warp per query -- the short lists of the filter rounds, and (dense_warp) the dense round's
     // too: thousands of independent warps re-reading a 32 KB list through L2 beat a CTA per query in barriers
-    if (B >= 128 && (fixed_count < 0 || dense_warp)) {
+    // (a warp holds up to 1024 keys in registers: lists of k (1 + 1.4 growth) keys with k in the hundreds fit; top-1000
+    // lists do not -- their warps fell back to re-reading the list from L2 in four radix passes, 9 ms of a 65 ms C5
+    // step -- so large k takes the CTA-per-query kernel, whose registers hold up to 16 K keys)
+    if (B >= 128 && (fixed_count < 0 || dense_warp) && K <= 256) {
         select_compact_warp_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(
             cand, cnt, cap, B, K, fixed_count, margin, thr, needed_cap, ovf, sx);
         return cudaGetLastError();
