@@ -67,6 +67,9 @@ SIGNATURES = {
     "hwer_ncf_param_count": (c_int64, [c_int32, c_int32]),
     "hwer_ncf_score": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                c_void_p]),
+    "hwer_gcn_infer": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                               c_void_p, c_void_p]),
     "hwer_eval_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "hwer_link_metrics": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhwer_b200.so")
-SOURCES = ["api.cu", "score_filter.cu", "select.cu", "exchange.cu", "blend_normalize.cu", "pair_eval.cu", "rerank.cu", "ncf.cu", "ncf_tc.cu",
+SOURCES = ["api.cu", "score_filter.cu", "select.cu", "exchange.cu", "blend_normalize.cu", "pair_eval.cu", "rerank.cu", "ncf.cu", "ncf_tc.cu", "gcn_infer.cu",
            "link_metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

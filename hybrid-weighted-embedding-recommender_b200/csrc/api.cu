@@ -905,6 +905,32 @@ int hwer_ncf_score(const float* h_dev, int64_t n_rows, int32_t F, int32_t depth,
     return HWER_OK;
 }
 
+int hwer_gcn_infer(const float* node_emb_dev, const float* content_dev, int64_t n, int32_t C, int32_t F, int32_t layers,
+                   const float* proj_w_dev, const float* proj_b_dev, const float* ln_g_dev, const float* ln_b_dev,
+                   const int64_t* const* nbr_ptr_dev, const int64_t* const* nbr_idx_dev, const float* fc0_w_dev,
+                   const float* fc0_b_dev, const float* fc1_w_dev, const float* fc1_b_dev, float* previous_dev, float ema,
+                   float* out_dev, void* stream_v) {
+    if (!node_emb_dev || !content_dev || !proj_w_dev || !proj_b_dev || !ln_g_dev || !ln_b_dev || !nbr_ptr_dev ||
+        !nbr_idx_dev || !fc0_w_dev || !fc0_b_dev || !fc1_w_dev || !fc1_b_dev || !out_dev || n < 0 || layers < 1 ||
+        layers > 8 || C < 4 || (C & 3) || F < 4 || (F & 3))
+        return fail(HWER_E_INVALID, "hwer_gcn_infer: bad argument (C and F must be positive multiples of 4, 1 <= layers <= 8)");
+    for (int i = 0; i < layers; ++i)
+        if (!nbr_ptr_dev[i] || !nbr_idx_dev[i]) return fail(HWER_E_INVALID, "hwer_gcn_infer: missing neighbour list");
+    if (n == 0) return HWER_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    long long chunk = 1 << 18;                                  // nodes per pass of the dense layers
+    if (chunk > n) chunk = n;
+    float* scratch = nullptr;
+    HWER_CUDA(cudaMallocAsync(&scratch, sizeof(float) * hwer::gcn_infer_scratch_floats(n, F, layers, chunk), stream));
+    cudaError_t e = hwer::launch_gcn_infer(node_emb_dev, content_dev, C, proj_w_dev, proj_b_dev, ln_g_dev, ln_b_dev, n, F,
+                                           layers, (const long long* const*)nbr_ptr_dev,
+                                           (const long long* const*)nbr_idx_dev, fc0_w_dev, fc0_b_dev, fc1_w_dev,
+                                           fc1_b_dev, previous_dev, ema, out_dev, scratch, chunk, stream);
+    cudaFreeAsync(scratch, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "hwer_gcn_infer");
+    return HWER_OK;
+}
+
 int hwer_eval_metrics(const int64_t* topk_dev, int32_t U, int32_t kret, const int64_t* train_ptr_dev,
                       const int64_t* train_idx_dev, const int64_t* val_ptr_dev, const int64_t* val_idx_dev,
                       const float* val_rel_dev, const int32_t* cutoffs_dev, int32_t n_cut, int64_t n_items,

@@ -206,4 +206,16 @@ cudaError_t launch_ncf_score_tc(const float* h, long long n_rows, int F, int dep
                                 const long long* src, const long long* dst, long long P, float* out, void* scratch,
                                 long long chunk, int num_sms, cudaStream_t stream);
 
+// fp32 GEMM of ncf.cu as a plain linear layer (gcn_infer.cu)
+cudaError_t launch_linear_f32(const float* x, const float* w, const float* b, float* y, long long P, int in, int out,
+                              float slope, cudaStream_t stream);
+
+// GCN inference over the whole graph with explicit per-block neighbour lists (gcn_infer.cu)
+size_t gcn_infer_scratch_floats(long long n, int F, int layers, long long chunk);
+cudaError_t launch_gcn_infer(const float* node_emb, const float* content, int C, const float* proj_w, const float* proj_b,
+                             const float* ln_g, const float* ln_b, long long n, int F, int layers,
+                             const long long* const* nbr_ptr, const long long* const* nbr_idx, const float* fc0_w,
+                             const float* fc0_b, const float* fc1_w, const float* fc1_b, float* previous, float ema,
+                             float* out, float* scratch, long long chunk, cudaStream_t stream);
+
 }  // namespace hwer

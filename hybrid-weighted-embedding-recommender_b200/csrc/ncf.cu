@@ -140,6 +140,20 @@ long long ncf_param_count(int F, int depth) {
     return n + F + 1;
 }
 
+// y[P, out] = LeakyReLU_slope(x[P, in] w^T + b) with the same FFMA GEMM (slope 1 = no activation); in and out must be
+// multiples of 4.  Used by the GCN inference path (gcn_infer.cu).
+cudaError_t launch_linear_f32(const float* x, const float* w, const float* b, float* y, long long P, int in, int out,
+                              float slope, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    if ((in & 3) || (out & 3)) return cudaErrorInvalidValue;
+    LinearArgs a;
+    a.x = x; a.h = nullptr; a.src = nullptr; a.dst = nullptr; a.n_rows = 0; a.F = 0;
+    a.in = in; a.out = out; a.w = w; a.b = b; a.y = y; a.P = P; a.slope = slope;
+    dim3 grid((unsigned)((out + BN - 1) / BN), (unsigned)((P + BM - 1) / BM));
+    ncf_linear_kernel<<<grid, kGemmThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ncf_score(const float* h, long long n_rows, int F, int depth, const float* params,
                              const long long* src, const long long* dst, long long P, float* out, float* ws0,
                              float* ws1, long long chunk, cudaStream_t stream) {

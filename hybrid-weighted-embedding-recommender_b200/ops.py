@@ -7,6 +7,7 @@ There is deliberately no CPU implementation: CPU tensors are rejected.
 import ctypes
 from ctypes import c_uint32, c_void_p
 
+import numpy as np
 import torch
 
 from . import _native as N
@@ -396,6 +397,80 @@ def ncf_score(h, params, src_rows, dst_rows, depth):
     with torch.cuda.device(h.device):
         N.check(N.lib().hwer_ncf_score(_dev_ptr(h), h.shape[0], F, int(depth), _dev_ptr(params), _dev_ptr(src_rows),
                                        _dev_ptr(dst_rows), P, _dev_ptr(out), _stream(h.device)))
+    return out
+
+
+def sample_neighbours(n, src, dst, fanout=2, seed=0, blocks=1):
+    """Host-side stand-in for the reference's DGL NeighborSampler(g, batch, 2, layers, add_self_loop=True)
+    (hwer/gcn_ncf.py:262-272): for each of `blocks` layers, up to `fanout` distinct random in-neighbours of every node
+    over the undirected edge list (src[i], dst[i]) plus a self loop, as CSR (ptr [n + 1], idx) int64 numpy arrays.
+    Seeded and vectorised (one random key per edge endpoint, the `fanout` smallest keys of every node win)."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    to = np.concatenate([dst, src])                      # in-neighbour lists of both directions (gcn.py:206-215)
+    frm = np.concatenate([src, dst])
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(int(blocks)):
+        key = rs.random_sample(to.shape[0])
+        order = np.lexsort((key, to))                    # by node, then by random key
+        to_s, frm_s = to[order], frm[order]
+        start = np.searchsorted(to_s, np.arange(n))      # first position of every node's run
+        rank = np.arange(to_s.shape[0]) - start[to_s]
+        keep = rank < fanout
+        picked_to, picked_from = to_s[keep], frm_s[keep]
+        all_to = np.concatenate([picked_to, np.arange(n, dtype=np.int64)])      # + self loops
+        all_from = np.concatenate([picked_from, np.arange(n, dtype=np.int64)])
+        o2 = np.argsort(all_to, kind="stable")
+        idx = all_from[o2]
+        ptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.bincount(all_to, minlength=n), out=ptr[1:])
+        out.append((ptr, idx))
+    return out
+
+
+def gcn_infer(node_emb, content, proj_w, proj_b, ln_g, ln_b, nbr, fc0_w, fc0_b, fc1_w, fc1_b, previous=None, ema=0.1):
+    """GraphConvModule.forward in eval mode over the whole graph (hwer/gcn.py:162-193; get_gcn_vectors,
+    hwer/gcn_ncf.py:260-279) with the neighbour sample of every block given as CSR lists `nbr[i] = (ptr, idx)`.
+    All tensors on one CUDA device, fp32 (lists int64); `previous` ([>= n, F]) is updated in place.
+    Returns h [n, F].  Widths that are not a multiple of 4 are zero-padded here (the result is unchanged)."""
+    node_emb = _need(node_emb, torch.float32, "node_emb", 2)
+    content = _need(content, torch.float32, "content", 2)
+    n, C = content.shape
+    F = node_emb.shape[1]
+    layers = len(nbr)
+    dev = content.device
+    proj_w = _need(proj_w, torch.float32, "proj_w", 2)
+    fc0_w = _need(fc0_w, torch.float32, "fc0_w", 2)
+    fc1_w = _need(fc1_w, torch.float32, "fc1_w", 2)
+    if node_emb.shape[0] < n + 1 or proj_w.shape != (F, C) or fc0_w.shape != (4 * F, F * (layers + 1)) or \
+            fc1_w.shape != (F, 4 * F):
+        raise ValueError("gcn_infer: parameter shapes do not match n=%d, C=%d, F=%d, layers=%d" % (n, C, F, layers))
+    if F % 4:
+        raise ValueError("gcn_infer: the feature width must be a multiple of 4 (the reference asserts a multiple of 16)")
+    if C % 4:                                            # zero columns of content / proj_w do not change the product
+        pad = 4 - C % 4
+        content = torch.nn.functional.pad(content, (0, pad)).contiguous()
+        proj_w = torch.nn.functional.pad(proj_w, (0, pad)).contiguous()
+        C += pad
+    vecs = [_need(t, torch.float32, name, 1) for t, name in ((proj_b, "proj_b"), (ln_g, "ln_g"), (ln_b, "ln_b"),
+                                                             (fc0_b, "fc0_b"), (fc1_b, "fc1_b"))]
+    ptrs = [_need(p, torch.int64, "nbr ptr", 1) for p, _ in nbr]
+    idxs = [_need(i, torch.int64, "nbr idx", 1) for _, i in nbr]
+    if any(p.shape[0] != n + 1 for p in ptrs):
+        raise ValueError("gcn_infer: every neighbour list needs n + 1 offsets")
+    if previous is not None:
+        previous = _need(previous, torch.float32, "previous", 2)
+        if previous.shape[0] < n or previous.shape[1] != F:
+            raise ValueError("gcn_infer: previous must be [>= n, F]")
+    out = torch.empty((n, F), dtype=torch.float32, device=dev)
+    p_arr = (ctypes.c_void_p * layers)(*[_dev_ptr(p) for p in ptrs])
+    i_arr = (ctypes.c_void_p * layers)(*[_dev_ptr(i) for i in idxs])
+    with torch.cuda.device(dev):
+        N.check(N.lib().hwer_gcn_infer(_dev_ptr(node_emb), _dev_ptr(content), n, C, F, layers, _dev_ptr(proj_w),
+                                       _dev_ptr(vecs[0]), _dev_ptr(vecs[1]), _dev_ptr(vecs[2]), p_arr, i_arr,
+                                       _dev_ptr(fc0_w), _dev_ptr(vecs[3]), _dev_ptr(fc1_w), _dev_ptr(vecs[4]),
+                                       _dev_ptr(previous), float(ema), _dev_ptr(out), _stream(dev)))
     return out
 
 

@@ -71,6 +71,38 @@ class GcnNCF(RecommendationBase):
         self.ncf_enabled = True
         return self
 
+    def get_gcn_vectors(self, gcn_params: Dict[str, object], content_vectors, edges: List[Edge] = None,
+                        neighbours=None, seed: int = 0, previous=None, ema: float = 0.1) -> torch.Tensor:
+        """The inference pass of the reference's get_gcn_vectors (hwer/gcn_ncf.py:260-279): the trained
+        GraphConvModule (hwer/gcn.py:146-193) applied to every node, producing the collaborative vectors that
+        prepare_for_knn turns into the serving table.  `gcn_params`: the module's tensors by name -- node_emb
+        [(n + 1), F], proj_w [F, C], proj_b, ln_g, ln_b [F], fc0_w [4F, F (layers + 1)], fc0_b, fc1_w [F, 4F], fc1_b
+        (torch state_dict entries `node_emb.weight`, `proj.0.*`, `proj.2.*`, `convs.<L-1>.fc.0.*`, `convs.<L-1>.fc.3.*`).
+        The neighbour sample of every block is either given (`neighbours`: one (ptr, idx) CSR pair per GCN layer) or
+        drawn here from `edges` like the reference's sampler does (two random in-neighbours + a self loop per node and
+        layer, seeded).  `previous`: the module's EMA state, updated in place."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+
+        def t(x, dtype=torch.float32):
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(np.ascontiguousarray(x))
+            return x.to(dev, dtype).contiguous()
+
+        g = {k_: t(v_) for k_, v_ in gcn_params.items()}
+        content = t(content_vectors)
+        layers = g["fc0_w"].shape[1] // g["node_emb"].shape[1] - 1
+        if neighbours is None:
+            assert edges is not None, "either `neighbours` or `edges` is needed"
+            src = self.nodes_to_idx.rows_of([e.src for e in edges])
+            dst = self.nodes_to_idx.rows_of([e.dst for e in edges])
+            neighbours = ops.sample_neighbours(content.shape[0], src, dst, fanout=2, seed=seed, blocks=layers)
+        nbr = [(t(p_, torch.int64), t(i_, torch.int64)) for p_, i_ in neighbours]
+        prev = None
+        if previous is not None:
+            prev = previous if isinstance(previous, torch.Tensor) and previous.is_cuda else t(previous)
+        return ops.gcn_infer(g["node_emb"], content, g["proj_w"], g["proj_b"], g["ln_g"], g["ln_b"], nbr, g["fc0_w"],
+                             g["fc0_b"], g["fc1_w"], g["fc1_b"], previous=prev, ema=ema)
+
     def predict_rows(self, src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
         if not self.ncf_enabled:
             return super().predict_rows(src_rows, dst_rows)

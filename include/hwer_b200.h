@@ -251,6 +251,21 @@ int64_t hwer_ncf_param_count(int32_t F, int32_t depth);
 int hwer_ncf_score(const float* h_dev, int64_t n_rows, int32_t F, int32_t depth, const float* params_dev,
                    const int64_t* src_dev, const int64_t* dst_dev, int64_t P, float* out_dev, void* stream);
 
+/* GCN inference: the collaborative table the serving path consumes, computed from a trained graph-convolution model.
+ * Replaces: get_gcn_vectors, hwer/gcn_ncf.py:260-279 = GraphConvModule.forward in eval mode, hwer/gcn.py:162-193
+ * (content projection gcn.py:40-44,59-63; GraphConv layers gcn.py:104-128; EMA with `previous` gcn.py:186-191), over
+ * the whole graph.  The neighbour sample of every block -- what DGL's NeighborSampler draws (two random in-neighbours
+ * and a self loop per node, gcn_ncf.py:262-272) -- is an input: nbr_ptr_dev[i] / nbr_idx_dev[i] are HOST arrays of
+ * `layers` device pointers, CSR over all n nodes (ptr [n + 1], idx node ids).
+ *   node_emb [(n + 1), F] (row v + 1 = node v, row 0 = padding node), content [n, C], proj_w [F, C], proj_b / ln_g /
+ *   ln_b [F], fc0_w [4F, F (layers + 1)], fc0_b [4F], fc1_w [F, 4F], fc1_b [F] (torch nn.Linear layouts),
+ *   previous [>= n, F] updated in place (NULL: no EMA), out [n, F].  C and F multiples of 4 (pad with zero columns). */
+int hwer_gcn_infer(const float* node_emb_dev, const float* content_dev, int64_t n, int32_t C, int32_t F, int32_t layers,
+                   const float* proj_w_dev, const float* proj_b_dev, const float* ln_g_dev, const float* ln_b_dev,
+                   const int64_t* const* nbr_ptr_dev, const int64_t* const* nbr_idx_dev, const float* fc0_w_dev,
+                   const float* fc0_b_dev, const float* fc1_w_dev, const float* fc1_b_dev, float* previous_dev, float ema,
+                   float* out_dev, void* stream);
+
 /* Ranking metrics for U users in one pass.
  * Replaces: the per-user loops of validation.extraction_efficiency, hwer/validation.py:133-174, with
  *           utils.reciprocal_rank / ndcg / binary_ndcg / recall, hwer/utils.py:71-121.

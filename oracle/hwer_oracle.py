@@ -429,3 +429,55 @@ def ncf_eval(model, train_edges, validation_edges, item_list, rng):
     hr = [actual[u] in top10[u] for u in actual]
     nd = [binary_ndcg_v2([actual[u]], top10[u]) for u in actual]
     return float(np.mean(hr)), float(np.mean(nd)), ranks
+
+
+# ------------------------------------------------------------------------------------------- GCN inference (8f rank 4)
+def gcn_infer(node_emb, content, proj_w, proj_b, ln_g, ln_b, nbr, fc0_w, fc0_b, fc1_w, fc1_b, previous=None, ema=0.1):
+    """Restatement of GraphConvModule.forward in eval mode (hwer/gcn.py:162-193) over the whole graph, with the
+    neighbour sample of every block given explicitly (`nbr[i] = (ptr [n+1], idx)`, self loop included) -- the form
+    get_gcn_vectors (hwer/gcn_ncf.py:260-279) takes when the NodeFlow covers every node.  fp32 like the reference.
+
+      h0[v]   = unit(node_emb[v + 1] + LayerNorm(LeakyReLU_0.1(content[v] W^T + b)))          gcn.py:40-44,59-63,170-175
+      H_i[v]  = [ mean_{u in nbr_i(v)} H_{i-1}[u]  ||  h0[v] ]                                 gcn.py:119-125,159-160
+      out[v]  = unit(fc1(LeakyReLU_0.01(fc0(H_L[v]))))                                         gcn.py:104-114,126-128
+      out[v]  = (1 - ema) out[v] + ema previous[v];  previous[v] = out[v]                      gcn.py:186-191
+    (unit() divides by max(norm, 1e-5); GaussianNoise is the identity in eval mode, gcn.py:32-37.)
+    Returns (out [n, F], previous_after or None)."""
+    f32 = np.float32
+    node_emb = np.asarray(node_emb, f32)
+    content = np.asarray(content, f32)
+    n = content.shape[0]
+
+    def unit(a):
+        nrm = np.sqrt((a * a).sum(axis=1, keepdims=True, dtype=f32)).astype(f32)
+        return (a / np.maximum(nrm, f32(1e-5))).astype(f32)
+
+    c = content @ np.asarray(proj_w, f32).T + np.asarray(proj_b, f32)
+    c = np.where(c > 0, c, f32(0.1) * c).astype(f32)
+    mu = c.mean(axis=1, keepdims=True, dtype=f32)
+    var = ((c - mu) ** 2).mean(axis=1, keepdims=True, dtype=f32)
+    c = ((c - mu) / np.sqrt(var + f32(1e-5)) * np.asarray(ln_g, f32) + np.asarray(ln_b, f32)).astype(f32)
+    h0 = unit(node_emb[1:n + 1] + c)
+    H = h0
+    for ptr, idx in nbr:
+        ptr = np.asarray(ptr, np.int64)
+        idx = np.asarray(idx, np.int64)
+        agg = np.zeros_like(H)
+        for v in range(n):
+            rows = idx[ptr[v]:ptr[v + 1]]
+            s = np.zeros(H.shape[1], f32)
+            for u in rows:                                   # list order, like DGL's sum reducer
+                s = s + H[u]
+            agg[v] = s / f32(len(rows))
+        H = np.concatenate([agg, h0], axis=1).astype(f32)
+    z = H @ np.asarray(fc0_w, f32).T + np.asarray(fc0_b, f32)
+    z = np.where(z > 0, z, f32(0.01) * z).astype(f32)
+    z = z @ np.asarray(fc1_w, f32).T + np.asarray(fc1_b, f32)
+    out = unit(z.astype(f32))
+    prev_after = None
+    if previous is not None:
+        previous = np.asarray(previous, f32)
+        out = (f32(1.0 - ema) * out + f32(ema) * previous[:n]).astype(f32)      # previous is indexed by node id, gcn.py:188
+        prev_after = previous.copy()
+        prev_after[:n] = out
+    return out, prev_after

@@ -84,6 +84,21 @@ def golden_c3():
 
 
 @pytest.fixture(scope="session")
+def golden_gcn():
+    return np.load(os.path.join(GOLDEN, "reference_gcn.npz"))
+
+
+def gcn_case(g, ci):
+    """Arguments of gcn_infer for case `ci` of reference_gcn.npz (oracle/make_golden_gcn.py)."""
+    p = "c%d_" % ci
+    n, C, F, L = [int(x) for x in g[p + "shape"]]
+    nbr = [(g[p + "nbr_ptr%d" % l], g[p + "nbr_idx%d" % l]) for l in range(L)]
+    names = ("node_emb", "content", "proj_w", "proj_b", "ln_g", "ln_b", "fc0_w", "fc0_b", "fc1_w", "fc1_b")
+    return dict(shape=(n, C, F, L), nbr=nbr, previous=g[p + "previous_before"], previous_after=g[p + "previous_after"],
+                h=g[p + "h"], **{k: g[p + k] for k in names})
+
+
+@pytest.fixture(scope="session")
 def golden_r2():
     return np.load(os.path.join(GOLDEN, "reference_r2.npz"))
 

@@ -209,3 +209,28 @@ def test_node_hash_is_recomputed_after_pickling_into_another_process():
         r = subprocess.run([sys.executable, "-c", code], input=blob, capture_output=True,
                            env=dict(os.environ, PYTHONHASHSEED=seed))
         assert r.returncode == 0 and b"ok" in r.stdout, r.stderr.decode()[-500:]
+
+
+def test_sample_neighbours_shape_and_determinism():
+    """Host stand-in for the reference's NeighborSampler (hwer/gcn_ncf.py:262-272): at most `fanout` distinct
+    in-neighbours over the undirected edge list + one self loop per node, one list per block, seeded."""
+    import hwer_b200 as hw
+    rs = np.random.RandomState(3)
+    n = 500
+    src, dst = rs.randint(0, n, 3000), rs.randint(0, n, 3000)
+    a = hw.ops.sample_neighbours(n, src, dst, fanout=2, seed=7, blocks=3)
+    b = hw.ops.sample_neighbours(n, src, dst, fanout=2, seed=7, blocks=3)
+    assert len(a) == 3
+    nbrs = [set() for _ in range(n)]
+    for s_, d_ in zip(src, dst):
+        nbrs[d_].add(int(s_))
+        nbrs[s_].add(int(d_))
+    for (p, i), (p2, i2) in zip(a, b):
+        assert np.array_equal(p, p2) and np.array_equal(i, i2)
+        assert p.shape == (n + 1,) and p[0] == 0 and p[-1] == i.shape[0]
+        for v in range(n):
+            row = i[p[v]:p[v + 1]].tolist()
+            assert row[-1] == v and 1 <= len(row) <= 3            # the self loop closes every list
+            assert all(u in nbrs[v] for u in row[:-1])
+            assert len(row) - 1 == min(2, sum(1 for s_, d_ in zip(src, dst) if d_ == v) + sum(1 for s_, d_ in zip(src, dst) if s_ == v))
+    assert any(not np.array_equal(a[0][1], a[k][1]) for k in (1, 2))    # blocks draw independently

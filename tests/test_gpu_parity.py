@@ -967,3 +967,58 @@ def test_full_size_properties_10m(hw):
                                           torch.stack([h[0] for h in parts]).contiguous(), want_f64=True)
         assert torch.equal(midx, idx4) and torch.equal(ms64, s4)
         del parts
+
+
+# ----------------------------------------------------------------------------- GCN inference
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_gcn_infer_matches_the_reference_module(hw, golden_gcn, ci):
+    """hwer_gcn_infer against outputs of the reference's GraphConvModule.forward (tests/golden/reference_gcn.npz,
+    oracle/make_golden_gcn.py; 1 / 2 / 3 GCN layers, content widths 48 / 20 / 36): node vectors and the EMA state.
+    fp32 tolerance 2e-6 (the kernels sum in a different order than torch's CPU GEMM)."""
+    from conftest import gcn_case
+    c = gcn_case(golden_gcn, ci)
+    t = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    prev = t(c["previous"])
+    nbr = [(t(p, torch.int64), t(i, torch.int64)) for p, i in c["nbr"]]
+    out = hw.ops.gcn_infer(t(c["node_emb"]), t(c["content"]), t(c["proj_w"]), t(c["proj_b"]), t(c["ln_g"]), t(c["ln_b"]),
+                           nbr, t(c["fc0_w"]), t(c["fc0_b"]), t(c["fc1_w"]), t(c["fc1_b"]), previous=prev, ema=0.1)
+    np.testing.assert_allclose(out.cpu().numpy(), c["h"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(prev.cpu().numpy(), c["previous_after"], rtol=0, atol=2e-6)
+
+
+def test_gcn_vectors_api_matches_oracle_and_feeds_the_search(hw):
+    """GcnNCF.get_gcn_vectors (neighbours drawn from the edge list by the host sampler, C = 50: not a multiple of 4,
+    several node chunks' worth of rows is covered by the golden cases' logic) == oracle.gcn_infer on the same lists;
+    and the vectors go through prepare_for_knn / __build_knn__ into a search like the reference's fit() does."""
+    rs = np.random.RandomState(31)
+    n_u, n_i, C, F, L = 300, 500, 50, 32, 2
+    n = n_u + n_i
+    users = [hw.Node("user", i) for i in range(n_u)]
+    items = [hw.Node("item", i) for i in range(n_i)]
+    edges = [hw.Edge(users[int(rs.randint(n_u))], items[int(rs.randint(n_i))], 1.0) for _ in range(4000)]
+    params = {"node_emb": rs.standard_normal((n + 1, F)).astype(np.float32) / F,
+              "proj_w": (rs.standard_normal((F, C)) * 0.2).astype(np.float32),
+              "proj_b": (rs.standard_normal(F) * 0.01).astype(np.float32),
+              "ln_g": (1 + 0.1 * rs.standard_normal(F)).astype(np.float32), "ln_b": (0.1 * rs.standard_normal(F)).astype(np.float32),
+              "fc0_w": (rs.standard_normal((4 * F, F * (L + 1))) * 0.1).astype(np.float32),
+              "fc0_b": (rs.standard_normal(4 * F) * 0.01).astype(np.float32),
+              "fc1_w": (rs.standard_normal((F, 4 * F)) * 0.1).astype(np.float32),
+              "fc1_b": (rs.standard_normal(F) * 0.01).astype(np.float32)}
+    content = rs.standard_normal((n, C)).astype(np.float32)
+    model = hw.GcnNCF(None, {"user", "item"}, n_dims=F)
+    model.add_nodes(users + items)
+    src = model.nodes_to_idx.rows_of([e.src for e in edges])
+    dst = model.nodes_to_idx.rows_of([e.dst for e in edges])
+    nbr = hw.ops.sample_neighbours(n, src, dst, fanout=2, seed=5, blocks=L)
+    got = model.get_gcn_vectors(params, content, edges=edges, seed=5)
+    want, _ = O.gcn_infer(params["node_emb"], content, params["proj_w"], params["proj_b"], params["ln_g"], params["ln_b"],
+                          nbr, params["fc0_w"], params["fc0_b"], params["fc1_w"], params["fc1_b"], None)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got.norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)      # no EMA: unit rows
+    # the same vectors, given explicitly, and into the serving table
+    got2 = model.get_gcn_vectors(params, content, neighbours=nbr)
+    assert torch.equal(got, got2)
+    served = hw.GcnNCF(None, {"user", "item"}, n_dims=F)
+    served.fit(users + items, edges, None, collaborative_vectors=got)
+    res = served.find_closest_neighbours("item", users[3], k=10)
+    assert len(res) == 10 and all(nd.node_type == "item" for nd, _ in res)

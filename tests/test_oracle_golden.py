@@ -328,3 +328,21 @@ def test_prepare_for_knn_pca_branch_matches_reference(golden_r2):
     np.testing.assert_allclose(got @ got.T, golden_r2["pca_table"] @ golden_r2["pca_table"].T, rtol=0, atol=2e-5)
     with pytest.raises(ValueError):
         O.prepare_for_knn(wide[:, :16], 32)
+
+
+# ----------------------------------------------------------------------------- GCN inference
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_gcn_infer_restatement_matches_the_reference_module(golden_gcn, ci):
+    """oracle.gcn_infer against outputs of the reference's own GraphConvModule.forward (hwer/gcn.py:162-193, 1 / 2 / 3
+    GCN layers), run in the build container on a stand-in NodeFlow with explicit neighbour lists
+    (oracle/make_golden_gcn.py): node vectors and the updated EMA state."""
+    from conftest import gcn_case
+    c = gcn_case(golden_gcn, ci)
+    out, prev = O.gcn_infer(c["node_emb"], c["content"], c["proj_w"], c["proj_b"], c["ln_g"], c["ln_b"], c["nbr"],
+                            c["fc0_w"], c["fc0_b"], c["fc1_w"], c["fc1_b"], c["previous"], 0.1)
+    np.testing.assert_allclose(out, c["h"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(prev, c["previous_after"], rtol=0, atol=1e-6)
+    n = c["shape"][0]
+    # rows are unit length before the EMA mixes 10 % of the previous state in: norms stay within that band
+    nrm = np.linalg.norm(out, axis=1)
+    assert nrm.max() < 1.0 + 0.1 * np.linalg.norm(c["previous"][:n], axis=1).max() + 1e-5
