@@ -46,19 +46,23 @@ pair_score_kernel(const float* __restrict__ table, long long n, int d, const lon
 // ---------------------------------------------------------------------------
 constexpr int kComposeMaxPerLane = 32;
 
+// PL = values per lane (d <= 32 * PL): 4 for the serving widths up to 128, 8 up to 256, 32 in general -- the general
+// shape keeps 64 accumulators per lane and 32 predicated loads per row, which left compose_queries at 9 % of the
+// copy bandwidth on 128-wide rows (bench.py aux_kernels, r2).
+template <int PL>
 __device__ __forceinline__ void mean_unit_accumulate(const float* __restrict__ table, long long n, int d,
                                                      const long long* __restrict__ rows, long long b, long long e,
-                                                     float sign, float (&acc)[kComposeMaxPerLane]) {
+                                                     float sign, float (&acc)[PL]) {
     const int lane = lane_id();
-    float m[kComposeMaxPerLane];
+    float m[PL];
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) m[j] = 0.f;
+    for (int j = 0; j < PL; ++j) m[j] = 0.f;
     for (long long i = b; i < e; ++i) {
         const long long r = rows[i];
         const bool unk = r < 0 || r >= n;
         const float* x = table + (size_t)(unk ? 0 : r) * d;
 #pragma unroll
-        for (int j = 0; j < kComposeMaxPerLane; ++j) {
+        for (int j = 0; j < PL; ++j) {
             const int c = lane + 32 * j;
             if (c < d) {
                 float v = x[c];
@@ -70,13 +74,14 @@ __device__ __forceinline__ void mean_unit_accumulate(const float* __restrict__ t
     const float inv_cnt = 1.0f / (float)(e - b);
     float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) { m[j] *= inv_cnt; ss = fmaf(m[j], m[j], ss); }
+    for (int j = 0; j < PL; ++j) { m[j] *= inv_cnt; ss = fmaf(m[j], m[j], ss); }
     ss = warp_sum(ss);
     const float inv_norm = sign / sqrtf(ss);
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) acc[j] = fmaf(m[j], inv_norm, acc[j]);
+    for (int j = 0; j < PL; ++j) acc[j] = fmaf(m[j], inv_norm, acc[j]);
 }
 
+template <int PL>
 __global__ void __launch_bounds__(256)
 compose_queries_kernel(const float* __restrict__ table, long long n, int d, const long long* __restrict__ anchor,
                        const long long* __restrict__ pos_ptr, const long long* __restrict__ pos_rows,
@@ -84,39 +89,40 @@ compose_queries_kernel(const float* __restrict__ table, long long n, int d, cons
                        float* __restrict__ out) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= B) return;
-    float acc[kComposeMaxPerLane];
+    float acc[PL];
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) acc[j] = 0.f;
+    for (int j = 0; j < PL; ++j) acc[j] = 0.f;
     int parts = 1;
-    mean_unit_accumulate(table, n, d, anchor, q, q + 1, 1.0f, acc);
+    mean_unit_accumulate<PL>(table, n, d, anchor, q, q + 1, 1.0f, acc);
     if (pos_ptr && pos_ptr[q + 1] > pos_ptr[q]) {
-        mean_unit_accumulate(table, n, d, pos_rows, pos_ptr[q], pos_ptr[q + 1], 1.0f, acc);
+        mean_unit_accumulate<PL>(table, n, d, pos_rows, pos_ptr[q], pos_ptr[q + 1], 1.0f, acc);
         ++parts;
     }
     if (neg_ptr && neg_ptr[q + 1] > neg_ptr[q]) {
-        mean_unit_accumulate(table, n, d, neg_rows, neg_ptr[q], neg_ptr[q + 1], -1.0f, acc);
+        mean_unit_accumulate<PL>(table, n, d, neg_rows, neg_ptr[q], neg_ptr[q + 1], -1.0f, acc);
         ++parts;
     }
     const float inv = 1.0f / (float)parts;
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) {
+    for (int j = 0; j < PL; ++j) {
         const int c = lane_id() + 32 * j;
         if (c < d) out[(size_t)q * d + c] = acc[j] * inv;
     }
 }
 
 // get_average_embeddings (hwer/recommendation_base.py:153-155): unit(mean(rows)) of each CSR list, one warp each.
+template <int PL>
 __global__ void __launch_bounds__(256)
 average_embeddings_kernel(const float* __restrict__ table, long long n, int d, const long long* __restrict__ ptr,
                           const long long* __restrict__ rows, int L, float* __restrict__ out) {
     const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (l >= L) return;
-    float acc[kComposeMaxPerLane];
+    float acc[PL];
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) acc[j] = 0.f;
-    mean_unit_accumulate(table, n, d, rows, ptr[l], ptr[l + 1], 1.0f, acc);     // empty list: 0/0 = NaN like numpy
+    for (int j = 0; j < PL; ++j) acc[j] = 0.f;
+    mean_unit_accumulate<PL>(table, n, d, rows, ptr[l], ptr[l + 1], 1.0f, acc);     // empty list: 0/0 = NaN like numpy
 #pragma unroll
-    for (int j = 0; j < kComposeMaxPerLane; ++j) {
+    for (int j = 0; j < PL; ++j) {
         const int c = lane_id() + 32 * j;
         if (c < d) out[(size_t)l * d + c] = acc[j];
     }
@@ -276,8 +282,11 @@ cudaError_t launch_compose_queries(const float* table, long long n, int d, const
                                    const long long* neg_rows, int B, float* out, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     if (d > 32 * kComposeMaxPerLane) return cudaErrorInvalidValue;
-    compose_queries_kernel<<<(B + 7) / 8, 256, 0, stream>>>(table, n, d, anchor, pos_ptr, pos_rows, neg_ptr, neg_rows, B,
-                                                            out);
+#define HWER_COMPOSE(PL)                                                                                              \
+    compose_queries_kernel<PL><<<(B + 7) / 8, 256, 0, stream>>>(table, n, d, anchor, pos_ptr, pos_rows, neg_ptr, neg_rows, \
+                                                                B, out)
+    if (d <= 128) HWER_COMPOSE(4); else if (d <= 256) HWER_COMPOSE(8); else HWER_COMPOSE(kComposeMaxPerLane);
+#undef HWER_COMPOSE
     return cudaGetLastError();
 }
 
@@ -285,7 +294,9 @@ cudaError_t launch_average_embeddings(const float* table, long long n, int d, co
                                       const long long* rows, int L, float* out, cudaStream_t stream) {
     if (L <= 0) return cudaSuccess;
     if (d > 32 * kComposeMaxPerLane) return cudaErrorInvalidValue;
-    average_embeddings_kernel<<<(L + 7) / 8, 256, 0, stream>>>(table, n, d, ptr, rows, L, out);
+    if (d <= 128) average_embeddings_kernel<4><<<(L + 7) / 8, 256, 0, stream>>>(table, n, d, ptr, rows, L, out);
+    else if (d <= 256) average_embeddings_kernel<8><<<(L + 7) / 8, 256, 0, stream>>>(table, n, d, ptr, rows, L, out);
+    else average_embeddings_kernel<kComposeMaxPerLane><<<(L + 7) / 8, 256, 0, stream>>>(table, n, d, ptr, rows, L, out);
     return cudaGetLastError();
 }
 

@@ -152,6 +152,23 @@ gather_rows_kernel(const float* __restrict__ table, long long n, int d, const lo
     }
 }
 
+// d % 4 == 0: a thread moves 16 bytes (one row id load per 4 columns instead of one per column)
+__global__ void __launch_bounds__(256)
+gather_rows_v4_kernel(const float* __restrict__ table, long long n, int d4, const long long* __restrict__ rows,
+                      long long P, float* __restrict__ out) {
+    const long long total = P * (long long)d4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / d4;
+        const int c = (int)(i - p * d4);
+        const long long r = rows[p];
+        const bool unk = r < 0 || r >= n;
+        float4 v = __ldg(reinterpret_cast<const float4*>(table) + (size_t)(unk ? 0 : r) * d4 + c);
+        if (unk) { v.x = unknown_clip_r(v.x); v.y = unknown_clip_r(v.y); v.z = unknown_clip_r(v.z); v.w = unknown_clip_r(v.w); }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
 // ncf_eval: scores [U, 1 + M], column 0 = the positive.  A stable descending sort keeps the positive ahead of
 // equal-scored negatives, so its rank is the number of strictly greater negatives.  One warp per user.
 __global__ void __launch_bounds__(256)
@@ -218,9 +235,11 @@ cudaError_t launch_map_rows(const long long* rows, long long count, const long l
 cudaError_t launch_gather_rows(const float* table, long long n, int d, const long long* rows, long long P, float* out,
                                cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
-    long long blocks = (P * d + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    gather_rows_kernel<<<(int)blocks, 256, 0, stream>>>(table, n, d, rows, P, out);
+    const bool v4 = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    long long blocks = (P * (v4 ? d / 4 : d) + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (v4) gather_rows_v4_kernel<<<(int)blocks, 256, 0, stream>>>(table, n, d / 4, rows, P, out);
+    else gather_rows_kernel<<<(int)blocks, 256, 0, stream>>>(table, n, d, rows, P, out);
     return cudaGetLastError();
 }
 
