@@ -85,6 +85,7 @@ struct hwer_index {
     // tuning knobs (HWER_FIRST_ROWS / HWER_GROWTH / HWER_LATE_ROWS), read once when the index is created
     long long env_first_rows = 0, env_late_rows = 0;
     int env_growth = 0;
+    long long env_narrow_tiles = 0;
     // HWER_DISABLE bit mask for A/B runs (measured in profiles/r02_*_ab.txt): 1 = bias MMA instead of scaled queries,
     // 2 = only the full-capacity final shape; and three alternatives that measured no better and are off by default:
     // 4 = warp-per-query final, 8 = spill extraction fused into the filter kernel, 16 = warp-per-query dense select;
@@ -328,6 +329,7 @@ int hwer_index_create(hwer_index_t** out, const float* table_f32_dev, const void
     if (const char* e = getenv("HWER_GROWTH")) ix->env_growth = atoi(e);
     if (const char* e = getenv("HWER_LATE_ROWS")) ix->env_late_rows = atoll(e);
     if (const char* e = getenv("HWER_DISABLE")) ix->env_disable = atoi(e);
+    if (const char* e = getenv("HWER_NARROW_TILES")) ix->env_narrow_tiles = atoll(e);
     *out = ix;
     return HWER_OK;
 }
@@ -424,7 +426,10 @@ int topk_impl(hwer_index_t* ix, const float* queries_dev, int32_t B, int32_t k, 
                 memset(&p, 0, sizeof p);
                 p.queries = Q; p.B = Bc; p.d = ix->d; p.kb = ix->d_pad / 64;
                 int nq = (Bc + 31) / 32 * 32;     // whole 32-column epilogue chunks
-                const int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
+                int nq_max = ix->d_pad > 192 ? 128 : hwer::kMaxNQ;
+                // A/B knob (HWER_NARROW_TILES = t): rounds of fewer than t tiles use 128-query blocks, i.e. four
+                // accumulator stages instead of two -- more room to absorb hit-handling latency where hits are dense
+                if (ix->env_narrow_tiles > 0 && round > 0 && (end - seen_l) < ix->env_narrow_tiles) nq_max = 128;
                 if (nq > nq_max) nq = nq_max;
                 p.nq = nq; p.nqb = (Bc + nq - 1) / nq;
                 // bf16 mode returns the tensor-core scores themselves: they must be products of the RN-bf16 query

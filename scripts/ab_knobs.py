@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--variants", default="3,0")
     ap.add_argument("--batches", default="4096,64,1")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--knob", default="HWER_DISABLE", help="the environment knob the variants are values of")
     ap.add_argument("--env", default="", help="extra knob per variant, e.g. 'HWER_GROWTH=4' applied to all")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -34,7 +35,7 @@ def main():
     ref = {}
     for rep in range(a.reps):
         for v in a.variants.split(","):
-            os.environ["HWER_DISABLE"] = v
+            os.environ[a.knob] = v
             index = hw.ops.TopKIndex(table, shadow, max_norm=1.0001)
             for B in [int(x) for x in a.batches.split(",")]:
                 steps = 8 if B >= 1024 else 40
