@@ -583,27 +583,33 @@ score_filter_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             for (int it = 0; it < my_tiles; ++it) {
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after_sync();
-                uint32_t v0[32], v1[32];
+                // ONE 32-column chunk is in registers at a time (r2): with both chunks live (64 value registers) the
+                // loop state spilled to local memory, and in hit-dense rounds those reloads queued behind the hit
+                // stores in the LSU -- the epilogue, not the tensor pipe, paced the round (ncu, round 3: 36 % tensor
+                // active, the hot stalls were LDL results).  The accumulator stage is released after the SECOND
+                // load, ~250 cycles later than before: still far inside the 1024 cycles the other stage's MMAs take.
+                uint32_t v[32];
                 const uint32_t taddr = tbase + acc * (uint32_t)nq;
-                tmem_ld_x32(taddr, v0);
-                if (two) tmem_ld_x32(taddr + 128u, v1);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);        // values are in registers: release the stage
-                if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
                 const uint32_t row = phys * (uint32_t)kTileItems + lane_row;
                 phys += tile_step;
                 if (phys >= tile_mod) phys -= tile_mod;
                 const bool row_ok = row < n_items;
                 const uint32_t dense_pos = (uint32_t)(t_first - p.tile_begin + it * work.t_stride) * (uint32_t)kTileItems + lane_row;
-                if (scaled) {
-                    epilogue_chunk<MODE, true>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
-                    if (two) epilogue_chunk<MODE, true>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
-                } else {
-                    epilogue_chunk<MODE, false>(v0, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
-                    if (two) epilogue_chunk<MODE, false>(v1, thr_s, c0 + 128, q_base, row, row_ok, p, sp, dense_pos);
+                tmem_ld_x32(taddr, v);
+                tmem_ld_wait();
+                if (two) {
+                    if (scaled) epilogue_chunk<MODE, true>(v, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
+                    else epilogue_chunk<MODE, false>(v, thr_s, c0, q_base, row, row_ok, p, sp, dense_pos);
+                    tmem_ld_x32(taddr + 128u, v);
+                    tmem_ld_wait();
                 }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);        // values are in registers: release the stage
+                if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                const int cc = two ? c0 + 128 : c0;
+                if (scaled) epilogue_chunk<MODE, true>(v, thr_s, cc, q_base, row, row_ok, p, sp, dense_pos);
+                else epilogue_chunk<MODE, false>(v, thr_s, cc, q_base, row, row_ok, p, sp, dense_pos);
             }
         }
         tiles_done += (uint32_t)my_tiles;
