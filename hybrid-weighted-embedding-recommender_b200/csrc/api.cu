@@ -197,8 +197,10 @@ struct Schedule {
 // (scripts/tune_schedule.py, profiles/r01_v6_tune.txt).
 int make_schedule(const hwer_index* ix, int B, int k, unsigned int cap_user, int world_share, Schedule* s) {
     const unsigned int max_cap = 16384;   // bounded by the shared-memory sort in select.cu
-    long long first_rows = (B > 512 || (B > 16 && B <= 128)) ? 4096 : 8192;
-    int g = B <= 16 ? 32 : (B <= 128 ? 16 : (B <= 512 ? 4 : 2));
+    // (re-tuned with the r2 kernels, profiles/r02_an_tune.txt: hits got cheaper, so batches up to 128 take growth 32
+    // after an 8192-row round 0 -- B = 64: 0.565 -> 0.50 ms per step; B = 4096 keeps 4096 rows / growth 2)
+    long long first_rows = B > 512 ? 4096 : 8192;
+    int g = B <= 128 ? 32 : (B <= 512 ? 4 : 2);
     // large batches of large k are bound by hit handling, not by launches: plain doubling admits 1.4 k per round
     // instead of 2.8 k (C5 shard, 62.5 M rows, k = 1000, B = 4096: 59.1 -> 58.2 ms per step; growth 3: 64.8 ms)
     if (B > 512 && k >= 512) g = 1;

@@ -149,10 +149,10 @@ def test_duplicates_follow_row_order_and_overflow_retries(hw):
     capacity exercise the HWER_E_OVERFLOW -> larger cap retry."""
     n, d, k = 30000, 128, 100
     t_np, _ = unit_table(n, d, 31)
-    t_np[5000:17000] = t_np[4999]                     # 12001 identical rows (> the automatic capacity of 8192 at B=40)
+    t_np[5000:17000] = t_np[4999]                     # 12001 identical rows (> the automatic capacity of 8192 at B=300)
     t_np[20000:20003] = t_np[7]
     t = torch.from_numpy(t_np).cuda()
-    q_np = np.concatenate([np.stack([t_np[4999], t_np[7], t_np[123]]), t_np[25000:25037]])
+    q_np = np.concatenate([np.stack([t_np[4999], t_np[7], t_np[123]]), t_np[25000:25297]])
     q = torch.from_numpy(q_np).cuda()
     index = hw.ops.TopKIndex(t)
     idx, sc = index.topk(q, k)
