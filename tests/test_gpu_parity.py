@@ -241,6 +241,20 @@ def _ids(res):
     return [int(n.node_external_id) for n, s in res], [float(s) for n, s in res]
 
 
+def test_batch_to_host_equals_the_plain_batch_call(c1_model):
+    """find_closest_neighbours_batch_to_host (chunked, result copies overlapped with the next chunk's search) returns
+    the rows, scores and order of the plain batched call, for Node anchors and for row tensors, any chunk size."""
+    m, users = c1_model["base"], c1_model["users"]
+    rows, sc = m.find_closest_neighbours_batch("item", users, k=10)
+    for chunk in (17, 256, 100000):
+        hr, hs = m.find_closest_neighbours_batch_to_host("item", users, k=10, chunk=chunk)
+        assert hr.is_pinned() and not hr.is_cuda
+        assert torch.equal(hr, rows.cpu()) and torch.equal(hs, sc.cpu())
+    arows = m._rows_of(users)
+    hr, hs = m.find_closest_neighbours_batch_to_host("item", arows, k=10, chunk=100)
+    assert torch.equal(hr, rows.cpu()) and torch.equal(hs, sc.cpu())
+
+
 def test_api_matches_reference_outputs(c1_model):
     m, g, k = c1_model["base"], c1_model["g"], c1_model["k"]
     users, items = c1_model["users"], c1_model["items"]
