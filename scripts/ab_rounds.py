@@ -40,12 +40,13 @@ def worker():
             index.topk_async(q, k)
         torch.cuda.synchronize()
         per = index.profile_launches()
+        st = {k_: round(v_ / steps, 4) for k_, v_ in index.profile_stages().items()}
         index.profile_read()
         index.profile(False)
         r = len(per) // steps
         rounds = [sum(per[s * r + i] for s in range(steps)) / steps * 1e3 for i in range(r)]
         out[str(B)] = {"step_ms": step_ms, "rounds_us": [round(x, 1) for x in rounds], "filter_ms": sum(rounds) / 1e3,
-                       "checksum": int(idx.sum().item())}
+                       "checksum": int(idx.sum().item()), "stages": st}
     print("RESULT " + json.dumps(out), flush=True)
 
 
@@ -64,8 +65,9 @@ def main():
     for B in ("4096", "64", "1"):
         for l in libs:
             for x in res[l]:
-                print("B=%-4s %-34s step %.3f ms filter %.3f ms rounds %s chk %d" % (
-                    B, os.path.basename(l), x[B]["step_ms"], x[B]["filter_ms"], x[B]["rounds_us"], x[B]["checksum"]))
+                print("B=%-4s %-34s step %.3f ms filter %.3f ms rounds %s chk %d stages %s" % (
+                    B, os.path.basename(l), x[B]["step_ms"], x[B]["filter_ms"], x[B]["rounds_us"], x[B]["checksum"],
+                    x[B].get("stages")))
 
 
 if __name__ == "__main__":
