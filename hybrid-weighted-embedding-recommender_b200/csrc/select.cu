@@ -601,6 +601,34 @@ __device__ __forceinline__ void exact_dot4_v4(const float* __restrict__ x0, cons
                                               const float4 (&qreg)[4], int nblk, double (&s)[4]) {
     s[0] = s[1] = s[2] = s[3] = 0.0;
     const int l = lane_id();
+    if (nblk == 2) {
+        // d = 256 (C3): both 128-column blocks of the four rows are requested before the first FMA -- eight loads in
+        // flight instead of two dependent rounds of four; the FMA order per candidate is unchanged (block 0 then
+        // block 1, x y z w), so the fp64 sums are the same bits
+        float4 a[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            a[b][0] = __ldg(reinterpret_cast<const float4*>(x0) + b * 32 + l);
+            a[b][1] = __ldg(reinterpret_cast<const float4*>(x1) + b * 32 + l);
+            a[b][2] = __ldg(reinterpret_cast<const float4*>(x2) + b * 32 + l);
+            a[b][3] = __ldg(reinterpret_cast<const float4*>(x3) + b * 32 + l);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const float4 q = qreg[b];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] = fma((double)a[b][j].x, (double)q.x, s[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] = fma((double)a[b][j].y, (double)q.y, s[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] = fma((double)a[b][j].z, (double)q.z, s[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] = fma((double)a[b][j].w, (double)q.w, s[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = warp_sum(s[j]);
+        return;
+    }
 #pragma unroll 1
     for (int b = 0; b < nblk; ++b) {
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(x0) + b * 32 + l);
